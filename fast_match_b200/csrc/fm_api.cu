@@ -1,0 +1,284 @@
+// fm_api.cu -- the extern "C" surface of libfmatch.so (see include/fastmatch_b200.h)
+// plus the small element-wise kernels (ratio test, shard merge).
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "fm_common.cuh"
+
+namespace fm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+constexpr unsigned long long NONE = 0xFFFFFFFFFFFFFFFFull;
+
+// Ratio test: fastmatch.pyx:124,165 / Classic Matching cell 3 (float32 sqrt, float64 divide).
+__global__ void k_ratio(const uint32_t *__restrict__ num_d2, int64_t num_stride,
+                        const uint32_t *__restrict__ den_d2, int64_t den_stride,
+                        const float *__restrict__ den_f32, int64_t M, double tau,
+                        double *__restrict__ ratio, uint8_t *__restrict__ mask) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t n = num_d2[i * num_stride];
+        uint32_t dd = den_f32 ? 0u : den_d2[i * den_stride];
+        double r;
+        if (n == FM_NONE_D2 || dd == FM_NONE_D2) {
+            r = __longlong_as_double(0x7FF0000000000000ll);
+        } else {
+            double num = (double)__fsqrt_rn((float)n);
+            double den = den_f32 ? (double)den_f32[i] : (double)__fsqrt_rn((float)dd);
+            r = __ddiv_rn(num, den);
+        }
+        if (ratio) ratio[i] = r;
+        if (mask) mask[i] = r < tau ? 1 : 0;
+    }
+}
+
+// Two smallest packed keys per query over S shards.
+__global__ void k_merge(const unsigned long long *__restrict__ keys, int32_t S, int64_t M,
+                        unsigned long long *__restrict__ out, uint32_t *__restrict__ d2,
+                        int32_t *__restrict__ idx) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long a = NONE, b = NONE;
+        for (int32_t s = 0; s < S; ++s) {
+            const ulonglong2 v = *(const ulonglong2 *)(keys + ((int64_t)s * M + i) * 2);
+            insert2(v.x, a, b);
+            insert2(v.y, a, b);
+        }
+        if (out) { out[2 * i] = a; out[2 * i + 1] = b; }
+        if (d2) { d2[2 * i] = (uint32_t)(a >> 32); d2[2 * i + 1] = (uint32_t)(b >> 32); }
+        if (idx) {
+            idx[2 * i] = a == NONE ? -1 : (int32_t)(uint32_t)a;
+            idx[2 * i + 1] = b == NONE ? -1 : (int32_t)(uint32_t)b;
+        }
+    }
+}
+
+__global__ void k_dist(const uint32_t *__restrict__ d2, float *__restrict__ dist, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = d2[i];
+        dist[i] = v == FM_NONE_D2 ? __int_as_float(0x7F800000) : __fsqrt_rn((float)v);
+    }
+}
+
+inline int grid_for(int64_t n, int block) {
+    int64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > 148 * 16) g = 148 * 16;
+    return (int)g;
+}
+
+inline bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace
+}  // namespace fm
+
+using namespace fm;
+
+extern "C" {
+
+int fm_version(void) { return 100; }
+
+const char *fm_last_error(void) { return fm::g_err; }
+
+int fm_device_caps(int device, int *sm_major, int *sm_minor, int *sm_count, int *has_tcgen05) {
+    cudaDeviceProp p;
+    FM_CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    if (sm_major) *sm_major = p.major;
+    if (sm_minor) *sm_minor = p.minor;
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (has_tcgen05) *has_tcgen05 = (p.major == 10) ? 1 : 0;
+    return FM_OK;
+}
+
+size_t fm_top2_workspace_bytes(int64_t M, int64_t N) { return fm::top2_tc_workspace_bytes(M, N); }
+
+int fm_top2_u8(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int32_t t_index_base,
+               uint32_t *d2, int32_t *idx, uint64_t *keys, void *ws, size_t ws_bytes, int algo,
+               void *stream) {
+    if (M < 0 || N < 0 || (M > 0 && (!q || !d2 || !idx)) || (N > 0 && !t)) {
+        set_error("fm_top2_u8: bad argument (M=%lld N=%lld q=%p t=%p d2=%p idx=%p)", (long long)M,
+                  (long long)N, (const void *)q, (const void *)t, (void *)d2, (void *)idx);
+        return FM_EINVAL;
+    }
+    if (!aligned16(q) || !aligned16(t)) {
+        set_error("fm_top2_u8: descriptor pointers must be 16-byte aligned");
+        return FM_EINVAL;
+    }
+    if (N + (int64_t)t_index_base > 0x7FFFFFFFll || M > 0x7FFFFFFFll) {
+        set_error("fm_top2_u8: index range exceeds int32");
+        return FM_EINVAL;
+    }
+    if (M == 0) return FM_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    bool use_tc;
+    if (algo == FM_ALGO_TCGEN05) {
+        if (!fm::tc_supported()) {
+            set_error("fm_top2_u8: FM_ALGO_TCGEN05 requested but the device is not sm_100");
+            return FM_EUNSUPPORTED;
+        }
+        use_tc = true;
+    } else if (algo == FM_ALGO_MMA_SYNC) {
+        use_tc = false;
+    } else if (algo == FM_ALGO_AUTO) {
+        // the tensor-core kernel pays a fixed set-up cost; tiny problems stay on the warp-MMA path
+        use_tc = fm::tc_supported() && N >= 256 && M * N >= (int64_t)1 << 20;
+    } else {
+        set_error("fm_top2_u8: unknown algo %d", algo);
+        return FM_EINVAL;
+    }
+    if (use_tc) {
+        if (ws_bytes < fm::top2_tc_workspace_bytes(M, N) || (!ws && fm::top2_tc_workspace_bytes(M, N))) {
+            set_error("fm_top2_u8: workspace too small (%zu < %zu)", ws_bytes,
+                      fm::top2_tc_workspace_bytes(M, N));
+            return FM_ENOSPACE;
+        }
+        return fm::launch_top2_tc(q, M, t, N, t_index_base, d2, idx, keys, ws, ws_bytes, s);
+    }
+    return fm::launch_sweep_mma_dense(q, M, t, N, t_index_base, d2, idx, keys, s);
+}
+
+int fm_ratio_f32sqrt(const uint32_t *num_d2, int64_t num_stride, const uint32_t *den_d2,
+                     int64_t den_stride, const float *den_f32, int64_t M, double tau,
+                     double *ratio, uint8_t *mask, void *stream) {
+    if (M < 0 || (M > 0 && (!num_d2 || (!den_d2 && !den_f32) || (!ratio && !mask)))) {
+        set_error("fm_ratio_f32sqrt: bad argument");
+        return FM_EINVAL;
+    }
+    if (M == 0) return FM_OK;
+    k_ratio<<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>(num_d2, num_stride, den_d2,
+                                                               den_stride, den_f32, M, tau, ratio,
+                                                               mask);
+    FM_CUDA_TRY(cudaGetLastError());
+    return FM_OK;
+}
+
+size_t fm_grouped_workspace_bytes(int64_t total_q, int64_t total_t, int32_t G) {
+    (void)total_q; (void)G;
+    return (size_t)(total_t > 0 ? total_t : 0) * sizeof(unsigned long long) + 16;
+}
+
+int fm_grouped_mutual_u8(const uint8_t *qpool, const int32_t *q_gather, const int64_t *q_off,
+                         const uint8_t *tpool, const int64_t *t_off, const int64_t *t_base,
+                         int32_t G, int64_t total_q,
+                         int64_t total_t, int32_t max_nq, uint32_t *q2t_d2, int32_t *q2t_idx,
+                         int32_t *t2q_idx, uint8_t *mutual, void *ws, size_t ws_bytes,
+                         void *stream) {
+    if (G < 0 || total_q < 0 || total_t < 0 || max_nq < 0 || (G > 0 && (!q_off || !t_off)) ||
+        (total_q > 0 && (!qpool || !q2t_d2 || !q2t_idx)) || (total_t > 0 && (!tpool || !t2q_idx))) {
+        set_error("fm_grouped_mutual_u8: bad argument");
+        return FM_EINVAL;
+    }
+    if (!aligned16(qpool) || !aligned16(tpool)) {
+        set_error("fm_grouped_mutual_u8: descriptor pointers must be 16-byte aligned");
+        return FM_EINVAL;
+    }
+    if (ws_bytes < fm_grouped_workspace_bytes(total_q, total_t, G) || !ws) {
+        set_error("fm_grouped_mutual_u8: workspace too small (%zu < %zu)", ws_bytes,
+                  fm_grouped_workspace_bytes(total_q, total_t, G));
+        return FM_ENOSPACE;
+    }
+    if (G == 0) return FM_OK;
+    return fm::launch_sweep_mma_grouped(qpool, q_gather, q_off, tpool, t_off, t_base, G, total_q, total_t,
+                                        max_nq, q2t_d2, q2t_idx, t2q_idx, mutual,
+                                        (unsigned long long *)ws, (cudaStream_t)stream);
+}
+
+int fm_merge_top2(const uint64_t *keys, int32_t S, int64_t M, uint64_t *out_keys, uint32_t *d2,
+                  int32_t *idx, void *stream) {
+    if (S < 0 || M < 0 || (M > 0 && S > 0 && !keys) || (!out_keys && !d2 && !idx)) {
+        set_error("fm_merge_top2: bad argument");
+        return FM_EINVAL;
+    }
+    if (M == 0) return FM_OK;
+    k_merge<<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const unsigned long long *)keys, S, M, (unsigned long long *)out_keys, d2, idx);
+    FM_CUDA_TRY(cudaGetLastError());
+    return FM_OK;
+}
+
+// ---- host-buffer convenience --------------------------------------------------------
+namespace {
+struct HostCtx {
+    std::mutex mu;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    uint8_t *pin_in = nullptr; size_t pin_in_cap = 0;
+    uint8_t *pin_out = nullptr; size_t pin_out_cap = 0;
+    uint8_t *dev = nullptr; size_t dev_cap = 0;
+};
+HostCtx g_host;
+
+int ensure(uint8_t **p, size_t *cap, size_t need, bool pinned) {
+    if (*cap >= need) return FM_OK;
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
+    size_t n = need + need / 4 + 4096;
+    if (pinned) FM_CUDA_TRY(cudaMallocHost((void **)p, n));
+    else FM_CUDA_TRY(cudaMalloc((void **)p, n));
+    *cap = n;
+    return FM_OK;
+}
+inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+}  // namespace
+
+int fm_top2_host_u8(const uint8_t *q_host, int64_t M, const uint8_t *t_host, int64_t N,
+                    uint32_t *d2_host, int32_t *idx_host, float *dist_host, int device) {
+    if (M < 0 || N < 0 || (M > 0 && (!q_host || !d2_host || !idx_host)) || (N > 0 && !t_host)) {
+        set_error("fm_top2_host_u8: bad argument");
+        return FM_EINVAL;
+    }
+    if (M == 0) return FM_OK;
+    HostCtx &c = g_host;
+    std::lock_guard<std::mutex> lock(c.mu);
+    FM_CUDA_TRY(cudaSetDevice(device));
+    if (c.device != device) {
+        if (c.stream) { cudaStreamDestroy(c.stream); c.stream = nullptr; }
+        if (c.dev) { cudaFree(c.dev); c.dev = nullptr; c.dev_cap = 0; }
+        FM_CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        c.device = device;
+    }
+    const size_t qb = (size_t)M * FM_DIM, tb = (size_t)N * FM_DIM;
+    const size_t ob_d2 = (size_t)M * 2 * 4, ob_idx = ob_d2, ob_dist = dist_host ? ob_d2 : 0;
+    const size_t wsb = fm_top2_workspace_bytes(M, N);
+    // device layout: q | t | d2 | idx | dist | ws
+    const size_t o_q = 0, o_t = up256(qb), o_d2 = o_t + up256(tb), o_idx = o_d2 + up256(ob_d2),
+                 o_dist = o_idx + up256(ob_idx), o_ws = o_dist + up256(ob_dist),
+                 total = o_ws + up256(wsb);
+    int rc;
+    if ((rc = ensure(&c.dev, &c.dev_cap, total, false)) != FM_OK) return rc;
+    if ((rc = ensure(&c.pin_in, &c.pin_in_cap, o_d2, true)) != FM_OK) return rc;
+    if ((rc = ensure(&c.pin_out, &c.pin_out_cap, o_ws - o_d2, true)) != FM_OK) return rc;
+    memcpy(c.pin_in + o_q, q_host, qb);
+    if (tb) memcpy(c.pin_in + o_t, t_host, tb);
+    FM_CUDA_TRY(cudaMemcpyAsync(c.dev, c.pin_in, o_t + tb, cudaMemcpyHostToDevice, c.stream));
+    rc = fm_top2_u8(c.dev + o_q, M, c.dev + o_t, N, 0, (uint32_t *)(c.dev + o_d2),
+                    (int32_t *)(c.dev + o_idx), nullptr, c.dev + o_ws, up256(wsb), FM_ALGO_AUTO,
+                    c.stream);
+    if (rc != FM_OK) return rc;
+    if (dist_host) {
+        k_dist<<<grid_for(M * 2, 256), 256, 0, c.stream>>>((const uint32_t *)(c.dev + o_d2),
+                                                          (float *)(c.dev + o_dist), M * 2);
+        FM_CUDA_TRY(cudaGetLastError());
+    }
+    FM_CUDA_TRY(cudaMemcpyAsync(c.pin_out, c.dev + o_d2, o_ws - o_d2, cudaMemcpyDeviceToHost,
+                                c.stream));
+    FM_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    memcpy(d2_host, c.pin_out, ob_d2);
+    memcpy(idx_host, c.pin_out + (o_idx - o_d2), ob_idx);
+    if (dist_host) memcpy(dist_host, c.pin_out + (o_dist - o_d2), ob_dist);
+    return FM_OK;
+}
+
+}  // extern "C"
