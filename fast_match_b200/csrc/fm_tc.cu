@@ -1,11 +1,550 @@
-// fm_tc.cu -- placeholder until the tcgen05 kernel lands (next commit).
+// fm_tc.cu -- dense exact top-2 on the 5th-generation tensor cores (sm_100a).
+//
+// Replaces cv2.BFMatcher(NORM_L2).knnMatch(q, t, k=2) (matchutil.py:39-43, Classic
+// Matching.ipynb cell 3) for large descriptor sets.  d2 = |q|^2 + |t|^2 - 2 q.t, with the
+// u8 x u8 -> s32 contraction on tcgen05.mma kind::i8; the M x N distance matrix only ever
+// exists as TMEM accumulators.
+//
+// Work decomposition
+//   * a CTA owns an M-block of 256 query rows = two 128-row sub-tiles whose descriptors stay
+//     resident in shared memory (TMA, 128B swizzle: one descriptor = one swizzle row);
+//   * target tiles of 256 descriptors (32 KB) stream through a 4-stage TMA ring; every tile
+//     is multiplied against both sub-tiles (4 x tcgen05.mma 128x256x32 each), so the two
+//     256-column TMEM accumulators ping-pong: while the epilogue drains sub-tile 0 the tensor
+//     core fills sub-tile 1;
+//   * grid = (M-blocks, N-splits): the target range is cut into `splits` slices so that the
+//     grid fills 148 SMs evenly; per-slice top-2 candidates are merged by fm_merge_top2's
+//     kernel (packed d2<<32|idx keys).
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4..19 = epilogue (TMEM lane quarter = warp % 4, column quarter = (warp-4) / 4).
+//
+// Epilogue: the per-output work has to stay near one instruction, so it is a filter.
+// For row i the candidates of a tile satisfy |t_j|^2 - 2 acc_ij >= tnmin(tile) - 2 max_j acc_ij,
+// hence a 32-column chunk can only change the row's top-2 if
+//     max_j acc_ij > (tnmin - m2) / 2          (m2 = current second-best partial distance)
+// The max over the chunk costs half an instruction per output (3-input max); the exact
+// insertion (strict "<", increasing j => ties keep the lowest index) runs only for chunks
+// that pass the filter, which becomes rare once m2 has tightened.  Results are exact.
+#include <cuda.h>
+
 #include "fm_common.cuh"
+
 namespace fm {
-bool tc_supported() { return false; }
-size_t top2_tc_workspace_bytes(int64_t, int64_t) { return 0; }
-int launch_top2_tc(const uint8_t *, int64_t, const uint8_t *, int64_t, int32_t, uint32_t *,
-                   int32_t *, uint64_t *, void *, size_t, cudaStream_t) {
-    set_error("tcgen05 kernel not built");
-    return FM_EUNSUPPORTED;
+
+namespace tc {
+
+constexpr int BM = 128;                 // rows per sub-tile (UMMA M)
+constexpr int SUBS = 2;                 // sub-tiles per CTA
+constexpr int BN = 256;                 // targets per tile (UMMA N)
+constexpr int STAGES = 4;
+constexpr int EPI_WARPS = 16;
+constexpr int NTHREADS = 128 + EPI_WARPS * 32;   // 640
+constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);  // 64
+constexpr int A_BYTES = BM * FM_DIM;    // 16 KB per sub-tile
+constexpr int B_BYTES = BN * FM_DIM;    // 32 KB per stage
+constexpr int TMEM_COLS = 512;
+
+struct __align__(8) Bars {
+    unsigned long long full[STAGES], empty[STAGES], a_full, tmem_full[SUBS], tmem_empty[SUBS];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+constexpr int SMEM_A = 0;
+constexpr int SMEM_B = SMEM_A + SUBS * A_BYTES;
+constexpr int SMEM_KEYS = SMEM_B + STAGES * B_BYTES;            // [256 rows][4 col quarters][2] u64
+constexpr int SMEM_BARS = SMEM_KEYS + SUBS * BM * 4 * 2 * 8;
+constexpr int SMEM_TOTAL = SMEM_BARS + (int)sizeof(Bars);
+constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;                   // slack for 1024-B alignment
+
+constexpr int I32_MAX = 0x7FFFFFFF;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must abort the kernel (trap), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity)) {
+        if ((++spins & 0xFFF) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();   // 4 s
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+                 "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, u8 x u8 -> s32, single-CTA
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                        uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                 ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+          "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+          "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+          "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);       // start address  [0,14)
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for SW128 K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset [32,46)
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+// kind::i8 instruction descriptor: D = s32, A = B = u8, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
+
+// ---------------------------------------------------------------------------------------------
+// pre-pass: squared norms (targets padded to whole tiles with INT_MAX), per-tile minimum
+// ---------------------------------------------------------------------------------------------
+__global__ void k_norms(const uint8_t *__restrict__ rows, int64_t n, int64_t n_padded,
+                        int *__restrict__ norms, int *__restrict__ tile_min) {
+    // 256 threads = 32 rows x 8 lanes(16 B); a block covers one 256-row tile in 8 passes
+    __shared__ int smin[8];
+    const int tid = threadIdx.x, sub = tid & 7, r = tid >> 3;
+    int mn = I32_MAX;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int64_t row = (int64_t)blockIdx.x * 256 + pass * 32 + r;
+        unsigned s = 0;
+        if (row < n) {
+            const uint4 x = *(const uint4 *)(rows + row * FM_DIM + sub * 16);
+            s = __dp4a(x.x, x.x, s); s = __dp4a(x.y, x.y, s);
+            s = __dp4a(x.z, x.z, s); s = __dp4a(x.w, x.w, s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (sub == 0 && row < n_padded) {
+            norms[row] = row < n ? (int)s : I32_MAX;
+            if (row < n) mn = min(mn, (int)s);
+        }
+    }
+    if (!tile_min) return;
+    for (int m = 16; m >= 1; m >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+    if ((tid & 31) == 0) smin[tid >> 5] = mn;
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < 8; ++i) mn = min(mn, smin[i]);
+        tile_min[blockIdx.x] = mn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------------
+struct RowState {
+    int m1, i1, m2, i2;   // best / second-best partial distance (|t|^2 - 2 q.t) and target index
+};
+
+__device__ __forceinline__ void slow_chunk(const int (&v)[32], const int *__restrict__ tn, int j0,
+                                           RowState &s) {
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        const int p = __ldg(tn + j0 + c) - 2 * v[c];
+        if (p < s.m2) {
+            if (p < s.m1) { s.m2 = s.m1; s.i2 = s.i1; s.m1 = p; s.i1 = j0 + c; }
+            else { s.m2 = p; s.i2 = j0 + c; }
+        }
+    }
+}
+
+__device__ __forceinline__ int chunk_max(const int (&v)[32]) {
+    int a = max3(v[0], v[1], v[2]), b = max3(v[3], v[4], v[5]), c = max3(v[6], v[7], v[8]);
+    int d = max3(v[9], v[10], v[11]), e = max3(v[12], v[13], v[14]), f = max3(v[15], v[16], v[17]);
+    int g = max3(v[18], v[19], v[20]), h = max3(v[21], v[22], v[23]), i = max3(v[24], v[25], v[26]);
+    int j = max3(v[27], v[28], v[29]), k = max(v[30], v[31]);
+    a = max3(a, b, c); d = max3(d, e, f); g = max3(g, h, i); j = max(j, k);
+    return max(max3(a, d, g), j);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
+          int64_t M, int64_t N, int32_t t_index_base, int ntiles_total, int splits,
+          const int *__restrict__ qn, const int *__restrict__ tn, const int *__restrict__ tile_min,
+          uint32_t *__restrict__ out_d2, int32_t *__restrict__ out_idx,
+          unsigned long long *__restrict__ out_keys, unsigned long long *__restrict__ partial) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    Bars *bars = (Bars *)(smem + SMEM_BARS);
+    unsigned long long *skeys = (unsigned long long *)(smem + SMEM_KEYS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mblock = blockIdx.x, split = blockIdx.y;
+    const int tile_begin = (int)((int64_t)ntiles_total * split / splits);
+    const int tile_end = (int)((int64_t)ntiles_total * (split + 1) / splits);
+    const int ntiles = tile_end - tile_begin;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+        mbar_init(smem_u32(&bars->a_full), 1);
+        for (int i = 0; i < SUBS; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_WARPS); }
+        fence_barrier_init();
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_t);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            const uint32_t abar = smem_u32(&bars->a_full);
+            mbar_expect_tx(abar, SUBS * A_BYTES);
+            for (int s = 0; s < SUBS; ++s)
+                tma_load_2d(smem_u32(smem + SMEM_A + s * A_BYTES), &map_q, 0,
+                            mblock * (SUBS * BM) + s * BM, abar);
+            for (int it = 0; it < ntiles; ++it) {
+                const int stage = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1);
+                const uint32_t fb = smem_u32(&bars->full[stage]);
+                mbar_expect_tx(fb, B_BYTES);
+                tma_load_2d(smem_u32(smem + SMEM_B + stage * B_BYTES), &map_t, 0,
+                            (tile_begin + it) * BN, fb);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(BM, BN);
+            mbar_wait(smem_u32(&bars->a_full), 0);
+            tc_fence_after();
+            for (int it = 0; it < ntiles; ++it) {
+                const int stage = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(smem_u32(&bars->full[stage]), ph);
+                tc_fence_after();
+                const uint64_t bdesc = make_desc(smem_u32(smem + SMEM_B + stage * B_BYTES));
+#pragma unroll
+                for (int s = 0; s < SUBS; ++s) {
+                    mbar_wait(smem_u32(&bars->tmem_empty[s]), (it & 1) ^ 1);
+                    tc_fence_after();
+                    const uint64_t adesc = make_desc(smem_u32(smem + SMEM_A + s * A_BYTES));
+#pragma unroll
+                    for (int k = 0; k < FM_DIM / 32; ++k)
+                        umma_i8(tmem_base + s * BN, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+                    umma_commit(smem_u32(&bars->tmem_full[s]));
+                }
+                umma_commit(smem_u32(&bars->empty[stage]));
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4;
+        const int lq = warp & 3;             // TMEM lane quarter this warp may touch
+        const int cq = ew >> 2;              // column quarter
+        const int row_in_sub = lq * 32 + lane;
+        RowState st[SUBS];
+#pragma unroll
+        for (int s = 0; s < SUBS; ++s) { st[s].m1 = st[s].m2 = I32_MAX; st[s].i1 = st[s].i2 = -1; }
+
+        for (int it = 0; it < ntiles; ++it) {
+            const int tile = tile_begin + it;
+            const int tmin = __ldg(tile_min + tile);
+            const int jbase = tile * BN + cq * COLS_PER_WARP;
+#pragma unroll
+            for (int s = 0; s < SUBS; ++s) {
+                mbar_wait(smem_u32(&bars->tmem_full[s]), it & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + s * BN + cq * COLS_PER_WARP;
+                int v0[32], v1[32];
+                tmem_ld32(taddr, v0);
+                tmem_ld32(taddr + 32, v1);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[s]));
+                // filter: can any of these 32 columns beat the current second best?
+                int thr = (tmin - st[s].m2) >> 1;
+                if (chunk_max(v0) > thr) {
+                    slow_chunk(v0, tn, jbase, st[s]);
+                    thr = (tmin - st[s].m2) >> 1;
+                }
+                if (chunk_max(v1) > thr) slow_chunk(v1, tn, jbase + 32, st[s]);
+            }
+        }
+        // ---- merge the 4 column quarters of every row through shared memory
+#pragma unroll
+        for (int s = 0; s < SUBS; ++s) {
+            const int r = s * BM + row_in_sub;
+            const int64_t grow = (int64_t)mblock * (SUBS * BM) + r;
+            const int qnr = grow < M ? __ldg(qn + grow) : 0;
+            unsigned long long k1 = st[s].i1 < 0 ? FM_NONE_KEY
+                : pack_key((uint32_t)(st[s].m1 + qnr), (uint32_t)(st[s].i1 + t_index_base));
+            unsigned long long k2 = st[s].i2 < 0 ? FM_NONE_KEY
+                : pack_key((uint32_t)(st[s].m2 + qnr), (uint32_t)(st[s].i2 + t_index_base));
+            skeys[(r * 4 + cq) * 2] = k1;
+            skeys[(r * 4 + cq) * 2 + 1] = k2;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        if (ew < 8) {
+            const int r = ew * 32 + lane;   // 256 rows, one thread each
+            const int64_t grow = (int64_t)mblock * (SUBS * BM) + r;
+            unsigned long long a = skeys[r * 8], b = skeys[r * 8 + 1];
+#pragma unroll
+            for (int c = 1; c < 4; ++c) merge2(a, b, skeys[r * 8 + 2 * c], skeys[r * 8 + 2 * c + 1]);
+            if (grow < M) {
+                if (partial) {
+                    partial[((int64_t)split * M + grow) * 2] = a;
+                    partial[((int64_t)split * M + grow) * 2 + 1] = b;
+                } else {
+                    out_d2[grow * 2] = (uint32_t)(a >> 32);
+                    out_d2[grow * 2 + 1] = (uint32_t)(b >> 32);
+                    out_idx[grow * 2] = a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a;
+                    out_idx[grow * 2 + 1] = b == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)b;
+                    if (out_keys) { out_keys[grow * 2] = a; out_keys[grow * 2 + 1] = b; }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// merge of the per-split partial keys (same semantics as fm_merge_top2)
+__global__ void k_merge_partial(const unsigned long long *__restrict__ partial, int splits,
+                                int64_t M, uint32_t *__restrict__ d2, int32_t *__restrict__ idx,
+                                unsigned long long *__restrict__ keys) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    unsigned long long a = FM_NONE_KEY, b = FM_NONE_KEY;
+    for (int s = 0; s < splits; ++s) {
+        const ulonglong2 v = *(const ulonglong2 *)(partial + ((int64_t)s * M + i) * 2);
+        insert2(v.x, a, b);
+        insert2(v.y, a, b);
+    }
+    d2[2 * i] = (uint32_t)(a >> 32);
+    d2[2 * i + 1] = (uint32_t)(b >> 32);
+    idx[2 * i] = a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a;
+    idx[2 * i + 1] = b == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)b;
+    if (keys) { keys[2 * i] = a; keys[2 * i + 1] = b; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap *map, const uint8_t *base, int64_t rows, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable"); return FM_ECUDA; }
+    cuuint64_t gdim[2] = {(cuuint64_t)FM_DIM, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)FM_DIM};
+    cuuint32_t box[2] = {(cuuint32_t)FM_DIM, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return FM_ECUDA; }
+    return FM_OK;
+}
+
+struct Plan {
+    int64_t mblocks, ntiles, npad;
+    int splits;
+    size_t off_tn, off_tmin, off_qn, off_partial, total;
+};
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+static Plan make_plan(int64_t M, int64_t N) {
+    Plan p;
+    p.mblocks = (M + SUBS * BM - 1) / (SUBS * BM);
+    p.ntiles = (N + BN - 1) / BN;
+    p.npad = p.ntiles * BN;
+    // choose the number of target slices that minimises (waves x tiles per CTA)
+    const int sms = sm_count();
+    int best = 1;
+    double best_cost = 1e300;
+    const int smax = (int)(p.ntiles < 32 ? (p.ntiles > 0 ? p.ntiles : 1) : 32);
+    for (int s = 1; s <= smax; ++s) {
+        const int64_t ctas = p.mblocks * s;
+        const int64_t waves = (ctas + sms - 1) / sms;
+        const double per_cta = (double)((p.ntiles + s - 1) / s) + 6.0;  // + fixed set-up, in tile units
+        const double cost = waves * per_cta;
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+    }
+    p.splits = best;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    p.off_tn = 0;
+    p.off_tmin = up(p.off_tn + (size_t)p.npad * 4);
+    p.off_qn = up(p.off_tmin + (size_t)(p.ntiles > 0 ? p.ntiles : 1) * 4);
+    p.off_partial = up(p.off_qn + (size_t)p.mblocks * SUBS * BM * 4);
+    p.total = up(p.off_partial + (p.splits > 1 ? (size_t)p.splits * M * 16 : 0));
+    return p;
+}
+
+}  // namespace tc
+
+bool tc_supported() {
+    static int ok = -1;
+    if (ok < 0) {
+        int dev = 0, major = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        ok = (major == 10 && tc::encode_fn() != nullptr) ? 1 : 0;
+    }
+    return ok == 1;
+}
+
+size_t top2_tc_workspace_bytes(int64_t M, int64_t N) {
+    if (M <= 0 || N <= 0) return 0;
+    return tc::make_plan(M, N).total;
+}
+
+int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int32_t t_index_base,
+                   uint32_t *d2, int32_t *idx, uint64_t *keys, void *ws, size_t ws_bytes,
+                   cudaStream_t s) {
+    using namespace tc;
+    if (N == 0) {  // nothing to match against: every slot is missing
+        FM_CUDA_TRY(cudaMemsetAsync(d2, 0xFF, (size_t)M * 8, s));
+        FM_CUDA_TRY(cudaMemsetAsync(idx, 0xFF, (size_t)M * 8, s));
+        if (keys) FM_CUDA_TRY(cudaMemsetAsync(keys, 0xFF, (size_t)M * 16, s));
+        return FM_OK;
+    }
+    const Plan p = make_plan(M, N);
+    if (ws_bytes < p.total) { set_error("tcgen05 path: workspace too small"); return FM_ENOSPACE; }
+    uint8_t *w = (uint8_t *)ws;
+    int *tn = (int *)(w + p.off_tn), *tmin = (int *)(w + p.off_tmin), *qn = (int *)(w + p.off_qn);
+    unsigned long long *partial = p.splits > 1 ? (unsigned long long *)(w + p.off_partial) : nullptr;
+
+    CUtensorMap map_q, map_t;
+    int rc;
+    if ((rc = make_map(&map_q, q, M, BM)) != FM_OK) return rc;
+    if ((rc = make_map(&map_t, t, N, BN)) != FM_OK) return rc;
+
+    k_norms<<<(unsigned)p.ntiles, 256, 0, s>>>(t, N, p.npad, tn, tmin);
+    k_norms<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(q, M, M, qn, nullptr);
+    FM_CUDA_TRY(cudaGetLastError());
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        FM_CUDA_TRY(cudaFuncSetAttribute(k_top2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)p.mblocks, (unsigned)p.splits);
+    k_top2_tc<<<grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, M, N, t_index_base, (int)p.ntiles,
+                                                 p.splits, qn, tn, tmin, d2, idx,
+                                                 (unsigned long long *)keys, partial);
+    FM_CUDA_TRY(cudaGetLastError());
+    if (partial) {
+        k_merge_partial<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(partial, p.splits, M, d2, idx,
+                                                                    (unsigned long long *)keys);
+        FM_CUDA_TRY(cudaGetLastError());
+    }
+    return FM_OK;
+}
+
 }  // namespace fm

@@ -25,7 +25,7 @@ def _check_top2(q, t, cuda, algo, base=0):
     assert np.array_equal(keys.cpu().numpy().view(np.uint64), oracle.pack_keys(od2, oidx))
 
 
-ALGOS = [backend.FM_ALGO_MMA_SYNC]
+ALGOS = [backend.FM_ALGO_MMA_SYNC, backend.FM_ALGO_TCGEN05]
 
 
 @pytest.mark.parametrize("algo", ALGOS)
