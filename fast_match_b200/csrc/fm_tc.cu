@@ -52,11 +52,13 @@ struct __align__(8) Bars {
 constexpr int SMEM_A = 0;
 constexpr int SMEM_B = SMEM_A + SUBS * A_BYTES;
 constexpr int SMEM_KEYS = SMEM_B + STAGES * B_BYTES;            // [256 rows][4 col quarters][2] u64
-constexpr int SMEM_BARS = SMEM_KEYS + SUBS * BM * 4 * 2 * 8;
+constexpr int SMEM_M2 = SMEM_KEYS + SUBS * BM * 4 * 2 * 8;      // [256 rows] shared second-best bound
+constexpr int SMEM_BARS = SMEM_M2 + SUBS * BM * 4;
 constexpr int SMEM_TOTAL = SMEM_BARS + (int)sizeof(Bars);
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;                   // slack for 1024-B alignment
 
 constexpr int I32_MAX = 0x7FFFFFFF;
+constexpr int NONE_P = 0x7FFFFF;   // "no candidate": above every real partial distance (<= 8323200)
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -175,10 +177,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
 // ---------------------------------------------------------------------------------------------
-// pre-pass: squared norms (targets padded to whole tiles with INT_MAX), per-tile minimum
+// pre-pass.  Targets: ckey[j] = |t_j|^2 * 256 + (j & 255) (INT_MAX on the padding up to a whole
+// tile) and the per-tile minimum of |t_j|^2.  Queries: plain squared norms.
 // ---------------------------------------------------------------------------------------------
+template <bool TARGETS>
 __global__ void k_norms(const uint8_t *__restrict__ rows, int64_t n, int64_t n_padded,
-                        int *__restrict__ norms, int *__restrict__ tile_min) {
+                        int *__restrict__ out, int *__restrict__ tile_min) {
     // 256 threads = 32 rows x 8 lanes(16 B); a block covers one 256-row tile in 8 passes
     __shared__ int smin[8];
     const int tid = threadIdx.x, sub = tid & 7, r = tid >> 3;
@@ -195,11 +199,12 @@ __global__ void k_norms(const uint8_t *__restrict__ rows, int64_t n, int64_t n_p
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         if (sub == 0 && row < n_padded) {
-            norms[row] = row < n ? (int)s : I32_MAX;
+            if (TARGETS) out[row] = row < n ? (int)s * 256 + (int)(row & 255) : I32_MAX;
+            else out[row] = (int)s;
             if (row < n) mn = min(mn, (int)s);
         }
     }
-    if (!tile_min) return;
+    if (!TARGETS) return;
     for (int m = 16; m >= 1; m >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, m));
     if ((tid & 31) == 0) smin[tid >> 5] = mn;
     __syncthreads();
@@ -216,31 +221,60 @@ struct RowState {
     int m1, i1, m2, i2;   // best / second-best partial distance (|t|^2 - 2 q.t) and target index
 };
 
-__device__ __forceinline__ void slow_chunk(const int (&v)[32], const int *__restrict__ tn, int j0,
-                                           RowState &s) {
+__device__ __forceinline__ int min3(int a, int b, int c) { return __vimin3_s32(a, b, c); }
+
+// Exact update of a row's top-2 from 16 accumulator columns.  key = partial * 256 + column
+// (unique inside a tile, so min/max on keys is the lexicographic (distance, index) order);
+// the chunk's own top-2 comes from a tree of sorted pairs, then merges into the row state with
+// strict "<" (targets stream in increasing index, so ties keep the lower index).
+__device__ __forceinline__ void slow16(const int *v, const int *__restrict__ ckey, int jtile,
+                                       RowState &s) {
+    int k[16];
+    const int4 *cp = (const int4 *)ckey;
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-        const int p = __ldg(tn + j0 + c) - 2 * v[c];
-        if (p < s.m2) {
-            if (p < s.m1) { s.m2 = s.m1; s.i2 = s.i1; s.m1 = p; s.i1 = j0 + c; }
-            else { s.m2 = p; s.i2 = j0 + c; }
+    for (int i = 0; i < 4; ++i) {
+        const int4 c = __ldg(cp + i);
+        k[4 * i + 0] = c.x - 512 * v[4 * i + 0];
+        k[4 * i + 1] = c.y - 512 * v[4 * i + 1];
+        k[4 * i + 2] = c.z - 512 * v[4 * i + 2];
+        k[4 * i + 3] = c.w - 512 * v[4 * i + 3];
+    }
+    int lo[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { lo[i] = min(k[2 * i], k[2 * i + 1]); hi[i] = max(k[2 * i], k[2 * i + 1]); }
+#pragma unroll
+    for (int w = 4; w >= 1; w >>= 1) {
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const int l = min(lo[i], lo[i + w]);
+            hi[i] = min3(max(lo[i], lo[i + w]), hi[i], hi[i + w]);
+            lo[i] = l;
+        }
+    }
+    const int p1 = lo[0] >> 8;
+    if (p1 < s.m2) {
+        const int j1 = jtile + (lo[0] & 255);
+        if (p1 < s.m1) {
+            const int p2 = hi[0] >> 8;
+            if (p2 < s.m1) { s.m2 = p2; s.i2 = jtile + (hi[0] & 255); }
+            else { s.m2 = s.m1; s.i2 = s.i1; }
+            s.m1 = p1; s.i1 = j1;
+        } else {
+            s.m2 = p1; s.i2 = j1;
         }
     }
 }
 
-__device__ __forceinline__ int chunk_max(const int (&v)[32]) {
-    int a = max3(v[0], v[1], v[2]), b = max3(v[3], v[4], v[5]), c = max3(v[6], v[7], v[8]);
-    int d = max3(v[9], v[10], v[11]), e = max3(v[12], v[13], v[14]), f = max3(v[15], v[16], v[17]);
-    int g = max3(v[18], v[19], v[20]), h = max3(v[21], v[22], v[23]), i = max3(v[24], v[25], v[26]);
-    int j = max3(v[27], v[28], v[29]), k = max(v[30], v[31]);
-    a = max3(a, b, c); d = max3(d, e, f); g = max3(g, h, i); j = max(j, k);
-    return max(max3(a, d, g), j);
+__device__ __forceinline__ int max16(const int *v) {
+    const int a = max3(v[0], v[1], v[2]), b = max3(v[3], v[4], v[5]), c = max3(v[6], v[7], v[8]);
+    const int d = max3(v[9], v[10], v[11]), e = max3(v[12], v[13], v[14]);
+    return max3(max3(a, b, c), max3(d, e, v[15]), a);
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
           int64_t M, int64_t N, int32_t t_index_base, int ntiles_total, int splits,
-          const int *__restrict__ qn, const int *__restrict__ tn, const int *__restrict__ tile_min,
+          const int *__restrict__ qn, const int *__restrict__ ckey, const int *__restrict__ tile_min,
           uint32_t *__restrict__ out_d2, int32_t *__restrict__ out_idx,
           unsigned long long *__restrict__ out_keys, unsigned long long *__restrict__ partial) {
     extern __shared__ uint8_t smem_raw[];
@@ -318,15 +352,24 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         const int cq = ew >> 2;              // column quarter
         const int row_in_sub = lq * 32 + lane;
         RowState st[SUBS];
+        int *sm2 = (int *)(smem + SMEM_M2);
 #pragma unroll
-        for (int s = 0; s < SUBS; ++s) { st[s].m1 = st[s].m2 = I32_MAX; st[s].i1 = st[s].i2 = -1; }
+        for (int s = 0; s < SUBS; ++s) {
+            st[s].m1 = st[s].m2 = NONE_P; st[s].i1 = st[s].i2 = -1;
+            if (cq == 0) sm2[s * BM + row_in_sub] = NONE_P;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
 
         for (int it = 0; it < ntiles; ++it) {
             const int tile = tile_begin + it;
             const int tmin = __ldg(tile_min + tile);
-            const int jbase = tile * BN + cq * COLS_PER_WARP;
+            const int jtile = tile * BN;
+            const int *ck = ckey + jtile + cq * COLS_PER_WARP;
 #pragma unroll
             for (int s = 0; s < SUBS; ++s) {
+                // Bound shared by the 4 warps that sweep this row's other column quarters.  It is
+                // applied non-strictly (+1): a sibling's candidate may carry a higher index.
+                const int shared_m2 = sm2[s * BM + row_in_sub];
                 mbar_wait(smem_u32(&bars->tmem_full[s]), it & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + s * BN + cq * COLS_PER_WARP;
@@ -337,13 +380,16 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[s]));
-                // filter: can any of these 32 columns beat the current second best?
-                int thr = (tmin - st[s].m2) >> 1;
-                if (chunk_max(v0) > thr) {
-                    slow_chunk(v0, tn, jbase, st[s]);
-                    thr = (tmin - st[s].m2) >> 1;
+                const int m2_before = st[s].m2;
+                int thr = (tmin - min(st[s].m2, shared_m2 + 1)) >> 1;
+#define FM_CHUNK(V, OFF)                                                                  \
+                if (max16(V + OFF) > thr) {                                                  \
+                    slow16(V + OFF, ck + (&V[0] == &v0[0] ? 0 : 32) + OFF, jtile, st[s]);    \
+                    thr = (tmin - min(st[s].m2, shared_m2 + 1)) >> 1;                        \
                 }
-                if (chunk_max(v1) > thr) slow_chunk(v1, tn, jbase + 32, st[s]);
+                FM_CHUNK(v0, 0) FM_CHUNK(v0, 16) FM_CHUNK(v1, 0) FM_CHUNK(v1, 16)
+#undef FM_CHUNK
+                if (st[s].m2 < m2_before) atomicMin(&sm2[s * BM + row_in_sub], st[s].m2);
             }
         }
         // ---- merge the 4 column quarters of every row through shared memory
@@ -525,8 +571,8 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     if ((rc = make_map(&map_q, q, M, BM)) != FM_OK) return rc;
     if ((rc = make_map(&map_t, t, N, BN)) != FM_OK) return rc;
 
-    k_norms<<<(unsigned)p.ntiles, 256, 0, s>>>(t, N, p.npad, tn, tmin);
-    k_norms<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(q, M, M, qn, nullptr);
+    k_norms<true><<<(unsigned)p.ntiles, 256, 0, s>>>(t, N, p.npad, tn, tmin);
+    k_norms<false><<<(unsigned)((M + 255) / 256), 256, 0, s>>>(q, M, M, qn, nullptr);
     FM_CUDA_TRY(cudaGetLastError());
 
     static bool attr_set = false;
