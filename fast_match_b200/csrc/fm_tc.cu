@@ -8,23 +8,27 @@
 // Work decomposition
 //   * a CTA owns an M-block of 256 query rows = two 128-row sub-tiles whose descriptors stay
 //     resident in shared memory (TMA, 128B swizzle: one descriptor = one swizzle row);
-//   * target tiles of 256 descriptors (32 KB) stream through a 4-stage TMA ring; every tile
-//     is multiplied against both sub-tiles (4 x tcgen05.mma 128x256x32 each), so the two
-//     256-column TMEM accumulators ping-pong: while the epilogue drains sub-tile 0 the tensor
-//     core fills sub-tile 1;
+//   * target tiles of 256 descriptors stream through a 4-stage TMA ring; every tile is
+//     multiplied against both sub-tiles, so the two 256-column TMEM accumulators ping-pong:
+//     while the epilogue drains sub-tile 0 the tensor core fills sub-tile 1;
 //   * grid = (M-blocks, N-splits): the target range is cut into `splits` slices so that the
-//     grid fills 148 SMs evenly; per-slice top-2 candidates are merged by fm_merge_top2's
-//     kernel (packed d2<<32|idx keys).
+//     grid fills the SMs evenly; per-slice candidates are merged by a small kernel.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
 // warps 4..19 = epilogue (TMEM lane quarter = warp % 4, column quarter = (warp-4) / 4).
 //
-// Epilogue: the per-output work has to stay near one instruction, so it is a filter.
-// For row i the candidates of a tile satisfy |t_j|^2 - 2 acc_ij >= tnmin(tile) - 2 max_j acc_ij,
-// hence a 32-column chunk can only change the row's top-2 if
-//     max_j acc_ij > (tnmin - m2) / 2          (m2 = current second-best partial distance)
-// The max over the chunk costs half an instruction per output (3-input max); the exact
-// insertion (strict "<", increasing j => ties keep the lowest index) runs only for chunks
-// that pass the filter, which becomes rare once m2 has tightened.  Results are exact.
+// The epilogue is the bottleneck (K is only 128: 512 tensor cycles per 32768 outputs, and the
+// integer min/max pipe retires 64 lanes/clk/SM), so the per-output work is ~0.5 instruction:
+//   * |t_j|^2 is folded into the contraction.  A fifth K-step multiplies a constant query-side
+//     block by 32 "digit" bytes per target that encode E_j = ceil((C - |t_j|^2)/2) (C = global
+//     constant), so the accumulator is acc'_ij = q_i.t_j + E_j and
+//         |t_j|^2 - 2 q_i.t_j  >=  C - 2 acc'_ij          (equality up to rounding of E_j)
+//     i.e. the largest accumulator of a row is its nearest neighbour (+25% MMA work buys a
+//     filter that needs no per-column term);
+//   * per 16 columns a 3-input max tree (0.5 op/output) is compared with the row's bound
+//     (C - m2)/2, m2 = current second-best partial distance (shared between the four warps
+//     that sweep the same row); only chunks that pass recompute exact integer keys
+//     (partial*256 + column) and update the row's top-2 with strict "<" in increasing column
+//     order, so ties keep the lowest index.  Results are exact for any u8 input.
 #include <cuda.h>
 
 #include "fm_common.cuh"
@@ -49,9 +53,13 @@ struct __align__(8) Bars {
     uint32_t tmem_base;
     uint32_t pad;
 };
+constexpr int AX_BYTES = BM * 32;       // constant query-side block of the norm K-step (4 KB)
+constexpr int BX_BYTES = BN * 32;       // per-target digit block of the norm K-step (8 KB / stage)
+constexpr int STAGE_BYTES = B_BYTES + BX_BYTES;
 constexpr int SMEM_A = 0;
-constexpr int SMEM_B = SMEM_A + SUBS * A_BYTES;
-constexpr int SMEM_KEYS = SMEM_B + STAGES * B_BYTES;            // [256 rows][4 col quarters][2] u64
+constexpr int SMEM_AX = SMEM_A + SUBS * A_BYTES;
+constexpr int SMEM_B = SMEM_AX + AX_BYTES;
+constexpr int SMEM_KEYS = SMEM_B + STAGES * STAGE_BYTES;        // [256 rows][4 col quarters][2] u64
 constexpr int SMEM_M2 = SMEM_KEYS + SUBS * BM * 4 * 2 * 8;      // [256 rows] shared second-best bound
 constexpr int SMEM_BARS = SMEM_M2 + SUBS * BM * 4;
 constexpr int SMEM_TOTAL = SMEM_BARS + (int)sizeof(Bars);
@@ -169,6 +177,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
     return d;
 }
+// K-major, 32-byte-swizzled operand tile: rows of 32 B (one K-step), 8-row groups 256 B apart.
+// The two 16-byte halves of every row hold the same bytes, so the swizzle's half-swap is moot.
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;                       // SWIZZLE_32B
+    return d;
+}
 // kind::i8 instruction descriptor: D = s32, A = B = u8, both K-major, M x N
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (2u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -177,41 +196,63 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
 // ---------------------------------------------------------------------------------------------
-// pre-pass.  Targets: ckey[j] = |t_j|^2 * 256 + (j & 255) (INT_MAX on the padding up to a whole
-// tile) and the per-tile minimum of |t_j|^2.  Queries: plain squared norms.
+// pre-pass
 // ---------------------------------------------------------------------------------------------
-template <bool TARGETS>
-__global__ void k_norms(const uint8_t *__restrict__ rows, int64_t n, int64_t n_padded,
-                        int *__restrict__ out, int *__restrict__ tile_min) {
-    // 256 threads = 32 rows x 8 lanes(16 B); a block covers one 256-row tile in 8 passes
-    __shared__ int smin[8];
-    const int tid = threadIdx.x, sub = tid & 7, r = tid >> 3;
-    int mn = I32_MAX;
-    for (int pass = 0; pass < 8; ++pass) {
-        const int64_t row = (int64_t)blockIdx.x * 256 + pass * 32 + r;
-        unsigned s = 0;
-        if (row < n) {
-            const uint4 x = *(const uint4 *)(rows + row * FM_DIM + sub * 16);
-            s = __dp4a(x.x, x.x, s); s = __dp4a(x.y, x.y, s);
-            s = __dp4a(x.z, x.z, s); s = __dp4a(x.w, x.w, s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (sub == 0 && row < n_padded) {
-            if (TARGETS) out[row] = row < n ? (int)s * 256 + (int)(row & 255) : I32_MAX;
-            else out[row] = (int)s;
-            if (row < n) mn = min(mn, (int)s);
-        }
+// squared norms of 128-byte rows; optional global minimum
+__global__ void k_norms(const uint8_t *__restrict__ rows, int64_t n, int *__restrict__ out,
+                        int *__restrict__ gmin) {
+    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t row = gt >> 3;
+    const int sub = (int)(gt & 7);
+    unsigned s = 0;
+    if (row < n) {
+        const uint4 x = *(const uint4 *)(rows + row * FM_DIM + sub * 16);
+        s = __dp4a(x.x, x.x, s); s = __dp4a(x.y, x.y, s);
+        s = __dp4a(x.z, x.z, s); s = __dp4a(x.w, x.w, s);
     }
-    if (!TARGETS) return;
-    for (int m = 16; m >= 1; m >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, m));
-    if ((tid & 31) == 0) smin[tid >> 5] = mn;
-    __syncthreads();
-    if (tid == 0) {
-        for (int i = 1; i < 8; ++i) mn = min(mn, smin[i]);
-        tile_min[blockIdx.x] = mn;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (sub == 0 && row < n) out[row] = (int)s;
+    if (gmin) {
+        int mn = row < n ? (int)s : I32_MAX;
+        for (int m = 16; m >= 1; m >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, m));
+        if ((threadIdx.x & 31) == 0 && mn != I32_MAX) atomicMin(gmin, mn);
     }
+}
+
+// Per target j: E_j = 2*ceil(max(C - tn_j, 0)/4) <= EMAX with C = gmin + 2*EMAX, written as 16
+// base-255 digits duplicated into both 16-byte halves of a 32-byte row (so the operand is
+// indifferent to the 32B swizzle), and the exact-key constant
+// ckey_j = (tn_j + 2 E_j) * 256 + (j & 255)  (wrapping int32; INT_MAX on the tile padding).
+constexpr int EHALF_MAX = 255 * 255 * 15 + 254;   // digits 0..14 weigh 255, digit 15 weighs 1
+constexpr int EMAX = 2 * EHALF_MAX;
+__global__ void k_target_aux(const int *__restrict__ tn, const int *__restrict__ gmin, int64_t n,
+                             int64_t n_padded, int *__restrict__ ckey, uint4 *__restrict__ digits,
+                             int *__restrict__ cg_out) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int cg = *gmin + 2 * EMAX;
+    if (j == 0) *cg_out = cg;
+    if (j >= n_padded) return;
+    if (j >= n) { ckey[j] = I32_MAX; return; }
+    const int t = tn[j];
+    const int e = cg - t;
+    int half = e > 0 ? (e + 3) >> 2 : 0;          // E_j / 2
+    if (half > EHALF_MAX) half = EHALF_MAX;        // cannot happen (e <= 2*EMAX), kept as a guard
+    ckey[j] = (int)(((unsigned)(t + 4 * half) << 8) | (unsigned)(j & 255));
+    int sdig = half / 255;
+    const unsigned r = (unsigned)(half - sdig * 255);
+    unsigned w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+        const int d = sdig > 255 ? 255 : sdig;
+        sdig -= d;
+        w[k >> 2] |= (unsigned)d << (8 * (k & 3));
+    }
+    w[3] |= r << 24;
+    const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+    digits[2 * j] = v;
+    digits[2 * j + 1] = v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -222,13 +263,20 @@ struct RowState {
 };
 
 __device__ __forceinline__ int min3(int a, int b, int c) { return __vimin3_s32(a, b, c); }
+__device__ __forceinline__ unsigned umin3(unsigned a, unsigned b, unsigned c) { return __vimin3_u32(a, b, c); }
 
-// Exact update of a row's top-2 from 16 accumulator columns.  key = partial * 256 + column
-// (unique inside a tile, so min/max on keys is the lexicographic (distance, index) order);
-// the chunk's own top-2 comes from a tree of sorted pairs, then merges into the row state with
-// strict "<" (targets stream in increasing index, so ties keep the lower index).
+__device__ __forceinline__ int max16(const int *v) {
+    const int a = max3(v[0], v[1], v[2]), b = max3(v[3], v[4], v[5]), c = max3(v[6], v[7], v[8]);
+    const int d = max3(v[9], v[10], v[11]), e = max3(v[12], v[13], v[14]);
+    return max3(max3(a, b, c), max3(d, e, v[15]), a);
+}
+
+// Exact update of a row's top-2 from 16 accumulator columns that passed the filter.
+// key = partial * 256 + column (unique inside a tile, so integer order on keys is the
+// lexicographic (distance, index) order).  `bound` <= s.m2, so a key below it enters the top-2;
+// the chunk's runner-up only matters when the chunk also produced a new best.
 __device__ __forceinline__ void slow16(const int *v, const int *__restrict__ ckey, int jtile,
-                                       RowState &s) {
+                                       int bound, RowState &s) {
     int k[16];
     const int4 *cp = (const int4 *)ckey;
 #pragma unroll
@@ -239,24 +287,25 @@ __device__ __forceinline__ void slow16(const int *v, const int *__restrict__ cke
         k[4 * i + 2] = c.z - 512 * v[4 * i + 2];
         k[4 * i + 3] = c.w - 512 * v[4 * i + 3];
     }
-    int lo[8], hi[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { lo[i] = min(k[2 * i], k[2 * i + 1]); hi[i] = max(k[2 * i], k[2 * i + 1]); }
-#pragma unroll
-    for (int w = 4; w >= 1; w >>= 1) {
-#pragma unroll
-        for (int i = 0; i < w; ++i) {
-            const int l = min(lo[i], lo[i + w]);
-            hi[i] = min3(max(lo[i], lo[i + w]), hi[i], hi[i + w]);
-            lo[i] = l;
-        }
-    }
-    const int p1 = lo[0] >> 8;
-    if (p1 < s.m2) {
-        const int j1 = jtile + (lo[0] & 255);
+    const int a = min3(k[0], k[1], k[2]), b = min3(k[3], k[4], k[5]), c = min3(k[6], k[7], k[8]);
+    const int d = min3(k[9], k[10], k[11]), e = min3(k[12], k[13], k[14]);
+    const int kmin = min3(min3(a, b, c), min3(d, e, k[15]), a);
+    const int p1 = kmin >> 8;
+    if (p1 < bound) {
+        const int j1 = jtile + (kmin & 255);
         if (p1 < s.m1) {
-            const int p2 = hi[0] >> 8;
-            if (p2 < s.m1) { s.m2 = p2; s.i2 = jtile + (hi[0] & 255); }
+            // runner-up of the chunk: smallest key above kmin (keys are distinct)
+            const int base = kmin + 1;
+            unsigned u[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) u[i] = (unsigned)(k[i] - base);   // kmin -> 0xFFFFFFFF
+            const unsigned ua = umin3(u[0], u[1], u[2]), ub = umin3(u[3], u[4], u[5]);
+            const unsigned uc = umin3(u[6], u[7], u[8]), ud = umin3(u[9], u[10], u[11]);
+            const unsigned ue = umin3(u[12], u[13], u[14]);
+            const unsigned um = umin3(umin3(ua, ub, uc), umin3(ud, ue, u[15]), ua);
+            const int k2 = (int)(um + (unsigned)base);
+            const int p2 = k2 >> 8;
+            if (p2 < s.m1) { s.m2 = p2; s.i2 = jtile + (k2 & 255); }
             else { s.m2 = s.m1; s.i2 = s.i1; }
             s.m1 = p1; s.i1 = j1;
         } else {
@@ -265,18 +314,13 @@ __device__ __forceinline__ void slow16(const int *v, const int *__restrict__ cke
     }
 }
 
-__device__ __forceinline__ int max16(const int *v) {
-    const int a = max3(v[0], v[1], v[2]), b = max3(v[3], v[4], v[5]), c = max3(v[6], v[7], v[8]);
-    const int d = max3(v[9], v[10], v[11]), e = max3(v[12], v[13], v[14]);
-    return max3(max3(a, b, c), max3(d, e, v[15]), a);
-}
-
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
-          int64_t M, int64_t N, int32_t t_index_base, int ntiles_total, int splits,
-          const int *__restrict__ qn, const int *__restrict__ ckey, const int *__restrict__ tile_min,
-          uint32_t *__restrict__ out_d2, int32_t *__restrict__ out_idx,
-          unsigned long long *__restrict__ out_keys, unsigned long long *__restrict__ partial) {
+          const __grid_constant__ CUtensorMap map_x, int64_t M, int64_t N, int32_t t_index_base,
+          int ntiles_total, int splits, const int *__restrict__ qn, const int *__restrict__ ckey,
+          const int *__restrict__ cg_ptr, uint32_t *__restrict__ out_d2,
+          int32_t *__restrict__ out_idx, unsigned long long *__restrict__ out_keys,
+          unsigned long long *__restrict__ partial) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     Bars *bars = (Bars *)(smem + SMEM_BARS);
@@ -295,8 +339,15 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         fence_barrier_init();
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_t);
+        tma_prefetch_desc(&map_x);
     }
     if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), TMEM_COLS);
+    if (threadIdx.x >= 128 && threadIdx.x < 128 + (AX_BYTES / 16)) {
+        // constant query-side block of the norm K-step: weights 255 (x15), 1 in both 16-B halves
+        *(uint4 *)(smem + SMEM_AX + (threadIdx.x - 128) * 16) =
+            make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0x01FFFFFFu);
+        fence_proxy_async();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -315,15 +366,17 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1);
                 const uint32_t fb = smem_u32(&bars->full[stage]);
-                mbar_expect_tx(fb, B_BYTES);
-                tma_load_2d(smem_u32(smem + SMEM_B + stage * B_BYTES), &map_t, 0,
-                            (tile_begin + it) * BN, fb);
+                mbar_expect_tx(fb, B_BYTES + BX_BYTES);
+                uint8_t *st = smem + SMEM_B + stage * STAGE_BYTES;
+                tma_load_2d(smem_u32(st), &map_t, 0, (tile_begin + it) * BN, fb);
+                tma_load_2d(smem_u32(st + B_BYTES), &map_x, 0, (tile_begin + it) * BN, fb);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BM, BN);
+            const uint64_t axdesc = make_desc_sw32(smem_u32(smem + SMEM_AX));
             mbar_wait(smem_u32(&bars->a_full), 0);
             tc_fence_after();
             for (int it = 0; it < ntiles; ++it) {
@@ -331,7 +384,9 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(smem_u32(&bars->full[stage]), ph);
                 tc_fence_after();
-                const uint64_t bdesc = make_desc(smem_u32(smem + SMEM_B + stage * B_BYTES));
+                const uint32_t sb = smem_u32(smem + SMEM_B + stage * STAGE_BYTES);
+                const uint64_t bdesc = make_desc(sb);
+                const uint64_t bxdesc = make_desc_sw32(sb + B_BYTES);
 #pragma unroll
                 for (int s = 0; s < SUBS; ++s) {
                     mbar_wait(smem_u32(&bars->tmem_empty[s]), (it & 1) ^ 1);
@@ -340,6 +395,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
 #pragma unroll
                     for (int k = 0; k < FM_DIM / 32; ++k)
                         umma_i8(tmem_base + s * BN, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+                    umma_i8(tmem_base + s * BN, axdesc, bxdesc, idesc, 1);   // + E_j
                     umma_commit(smem_u32(&bars->tmem_full[s]));
                 }
                 umma_commit(smem_u32(&bars->empty[stage]));
@@ -351,6 +407,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         const int lq = warp & 3;             // TMEM lane quarter this warp may touch
         const int cq = ew >> 2;              // column quarter
         const int row_in_sub = lq * 32 + lane;
+        const int cg = __ldg(cg_ptr);
         RowState st[SUBS];
         int *sm2 = (int *)(smem + SMEM_M2);
 #pragma unroll
@@ -361,9 +418,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
 
         for (int it = 0; it < ntiles; ++it) {
-            const int tile = tile_begin + it;
-            const int tmin = __ldg(tile_min + tile);
-            const int jtile = tile * BN;
+            const int jtile = (tile_begin + it) * BN;
             const int *ck = ckey + jtile + cq * COLS_PER_WARP;
 #pragma unroll
             for (int s = 0; s < SUBS; ++s) {
@@ -381,13 +436,15 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[s]));
                 const int m2_before = st[s].m2;
-                int thr = (tmin - min(st[s].m2, shared_m2 + 1)) >> 1;
-#define FM_CHUNK(V, OFF)                                                                  \
-                if (max16(V + OFF) > thr) {                                                  \
-                    slow16(V + OFF, ck + (&V[0] == &v0[0] ? 0 : 32) + OFF, jtile, st[s]);    \
-                    thr = (tmin - min(st[s].m2, shared_m2 + 1)) >> 1;                        \
+                int bound = min(st[s].m2, shared_m2 + 1);
+                int thr = (cg - bound) >> 1;        // acc' > thr  <=>  C - 2 acc' < bound
+#define FM_CHUNK(V, COL)                                                        \
+                if (max16(V + ((COL) & 31)) > thr) {                               \
+                    slow16(V + ((COL) & 31), ck + (COL), jtile, bound, st[s]);     \
+                    bound = min(st[s].m2, shared_m2 + 1);                          \
+                    thr = (cg - bound) >> 1;                                       \
                 }
-                FM_CHUNK(v0, 0) FM_CHUNK(v0, 16) FM_CHUNK(v1, 0) FM_CHUNK(v1, 16)
+                FM_CHUNK(v0, 0) FM_CHUNK(v0, 16) FM_CHUNK(v1, 32) FM_CHUNK(v1, 48)
 #undef FM_CHUNK
                 if (st[s].m2 < m2_before) atomicMin(&sm2[s * BM + row_in_sub], st[s].m2);
             }
@@ -474,16 +531,17 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap *map, const uint8_t *base, int64_t rows, int box_rows) {
+static int make_map(CUtensorMap *map, const uint8_t *base, int64_t rows, int row_bytes,
+                    int box_rows, CUtensorMapSwizzle swz) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable"); return FM_ECUDA; }
-    cuuint64_t gdim[2] = {(cuuint64_t)FM_DIM, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)FM_DIM};
-    cuuint32_t box[2] = {(cuuint32_t)FM_DIM, (cuuint32_t)box_rows};
+    cuuint64_t gdim[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)row_bytes, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)base, gdim, gstride, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return FM_ECUDA; }
     return FM_OK;
 }
@@ -491,7 +549,7 @@ static int make_map(CUtensorMap *map, const uint8_t *base, int64_t rows, int box
 struct Plan {
     int64_t mblocks, ntiles, npad;
     int splits;
-    size_t off_tn, off_tmin, off_qn, off_partial, total;
+    size_t off_tn, off_ckey, off_digits, off_scal, off_qn, off_partial, total;
 };
 
 static int sm_count() {
@@ -525,8 +583,10 @@ static Plan make_plan(int64_t M, int64_t N) {
     p.splits = best;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     p.off_tn = 0;
-    p.off_tmin = up(p.off_tn + (size_t)p.npad * 4);
-    p.off_qn = up(p.off_tmin + (size_t)(p.ntiles > 0 ? p.ntiles : 1) * 4);
+    p.off_ckey = up(p.off_tn + (size_t)p.npad * 4);
+    p.off_digits = up(p.off_ckey + (size_t)p.npad * 4);
+    p.off_scal = up(p.off_digits + (size_t)p.npad * 32);        // [0] = min |t|^2, [1] = C
+    p.off_qn = up(p.off_scal + 256);
     p.off_partial = up(p.off_qn + (size_t)p.mblocks * SUBS * BM * 4);
     p.total = up(p.off_partial + (p.splits > 1 ? (size_t)p.splits * M * 16 : 0));
     return p;
@@ -563,16 +623,22 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     const Plan p = make_plan(M, N);
     if (ws_bytes < p.total) { set_error("tcgen05 path: workspace too small"); return FM_ENOSPACE; }
     uint8_t *w = (uint8_t *)ws;
-    int *tn = (int *)(w + p.off_tn), *tmin = (int *)(w + p.off_tmin), *qn = (int *)(w + p.off_qn);
+    int *tn = (int *)(w + p.off_tn), *ckey = (int *)(w + p.off_ckey), *qn = (int *)(w + p.off_qn);
+    int *scal = (int *)(w + p.off_scal);
+    uint8_t *digits = w + p.off_digits;
     unsigned long long *partial = p.splits > 1 ? (unsigned long long *)(w + p.off_partial) : nullptr;
 
-    CUtensorMap map_q, map_t;
+    CUtensorMap map_q, map_t, map_x;
     int rc;
-    if ((rc = make_map(&map_q, q, M, BM)) != FM_OK) return rc;
-    if ((rc = make_map(&map_t, t, N, BN)) != FM_OK) return rc;
+    if ((rc = make_map(&map_q, q, M, FM_DIM, BM, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
+    if ((rc = make_map(&map_t, t, N, FM_DIM, BN, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
+    if ((rc = make_map(&map_x, digits, N, 32, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) != FM_OK) return rc;
 
-    k_norms<true><<<(unsigned)p.ntiles, 256, 0, s>>>(t, N, p.npad, tn, tmin);
-    k_norms<false><<<(unsigned)((M + 255) / 256), 256, 0, s>>>(q, M, M, qn, nullptr);
+    FM_CUDA_TRY(cudaMemsetAsync(scal, 0x7F, 8, s));
+    k_norms<<<(unsigned)((N * 8 + 255) / 256), 256, 0, s>>>(t, N, tn, scal);
+    k_norms<<<(unsigned)((M * 8 + 255) / 256), 256, 0, s>>>(q, M, qn, nullptr);
+    k_target_aux<<<(unsigned)((p.npad + 255) / 256), 256, 0, s>>>(tn, scal, N, p.npad, ckey,
+                                                                 (uint4 *)digits, scal + 1);
     FM_CUDA_TRY(cudaGetLastError());
 
     static bool attr_set = false;
@@ -581,9 +647,9 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
         attr_set = true;
     }
     dim3 grid((unsigned)p.mblocks, (unsigned)p.splits);
-    k_top2_tc<<<grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, M, N, t_index_base, (int)p.ntiles,
-                                                 p.splits, qn, tn, tmin, d2, idx,
-                                                 (unsigned long long *)keys, partial);
+    k_top2_tc<<<grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base,
+                                                 (int)p.ntiles, p.splits, qn, ckey, scal + 1, d2,
+                                                 idx, (unsigned long long *)keys, partial);
     FM_CUDA_TRY(cudaGetLastError());
     if (partial) {
         k_merge_partial<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(partial, p.splits, M, d2, idx,
