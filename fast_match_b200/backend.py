@@ -24,7 +24,7 @@ class FastMatchError(RuntimeError):
 def lib():
     global _lib
     if _lib is None:
-        path = _build.LIB
+        path = os.environ.get("FM_LIB", _build.LIB)   # FM_LIB: instrumented builds (tools/ only)
         if not os.path.exists(path):
             raise FastMatchError(
                 "libfmatch.so is not built (%s); run `python -m fast_match_b200.build` -- "
@@ -43,7 +43,10 @@ def lib():
         L.fm_grouped_mutual_u8.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i64, i32, vp, vp, vp, vp,
                                            vp, sz, vp]
         L.fm_merge_top2.argtypes = [vp, i32, i64, vp, vp, vp, vp]
-        L.fm_top2_host_u8.argtypes = [vp, i64, vp, i64, vp, vp, vp, ctypes.c_int]
+        L.fm_top2_host_u8.argtypes = [vp, i64, vp, i64, vp, vp, vp, ctypes.c_double, vp, ctypes.c_int]
+        L.fm_launch_count.restype = ctypes.c_longlong
+        L.fm_profile_enable.argtypes = [ctypes.c_int]
+        L.fm_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
         _lib = L
     return _lib
 
@@ -182,20 +185,44 @@ def merge_top2(keys, want_unpacked=True):
     return out, d2, idx
 
 
-def top2_host(q_np, t_np, device=0, want_dist=True):
-    """numpy in / numpy out through fm_top2_host_u8 (H2D + kernel + D2H inside the call)."""
+def top2_host(q_np, t_np, device=0, want_dist=True, tau=None, out=None):
+    """numpy in / numpy out through fm_top2_host_u8 (H2D + kernels + D2H inside the call).
+    tau: also return the Lowe ratio-test mask.  out: (d2, idx, dist|None, mask|None) buffers to
+    reuse (pinned buffers are used directly by the library)."""
     import numpy as np
     q_np = np.ascontiguousarray(q_np, dtype=np.uint8)
     t_np = np.ascontiguousarray(t_np, dtype=np.uint8)
     if q_np.ndim != 2 or q_np.shape[1] != 128 or t_np.ndim != 2 or t_np.shape[1] != 128:
         raise FastMatchError("descriptors must have shape [n, 128]")
     M, N = len(q_np), len(t_np)
-    d2 = np.empty((M, 2), np.uint32)
-    idx = np.empty((M, 2), np.int32)
-    dist = np.empty((M, 2), np.float32) if want_dist else None
+    if out is None:
+        d2 = np.empty((M, 2), np.uint32)
+        idx = np.empty((M, 2), np.int32)
+        dist = np.empty((M, 2), np.float32) if want_dist else None
+        mask = np.empty(M, np.uint8) if tau is not None else None
+    else:
+        d2, idx, dist, mask = out
     vp = ctypes.c_void_p
     _check(lib().fm_top2_host_u8(q_np.ctypes.data_as(vp), M, t_np.ctypes.data_as(vp), N,
                                  d2.ctypes.data_as(vp), idx.ctypes.data_as(vp),
-                                 None if dist is None else dist.ctypes.data_as(vp), int(device)),
+                                 None if dist is None else dist.ctypes.data_as(vp),
+                                 float(tau if tau is not None else 0.0),
+                                 None if mask is None else mask.ctypes.data_as(vp), int(device)),
            "fm_top2_host_u8")
+    if tau is not None:
+        return d2, idx, dist, mask
     return d2, idx, dist
+
+
+def launch_count():
+    return int(lib().fm_launch_count())
+
+
+def profile_enable(on=True):
+    lib().fm_profile_enable(1 if on else 0)
+
+
+def profile_read(reset=True):
+    ms, n = ctypes.c_double(), ctypes.c_int()
+    _check(lib().fm_profile_read(ctypes.byref(ms), ctypes.byref(n), 1 if reset else 0), "fm_profile_read")
+    return ms.value, n.value

@@ -20,19 +20,22 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile csrc/*.cu into libfmatch.so.  `defines`/`out` build instrumented variants
+    (e.g. -DFM_TC_PROF -> libfmatch_prof.so, used only by tools/)."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-I" + INCLUDE, "-o", LIB] + sources()
+           "-Xcompiler", "-fPIC", "-shared", "-I" + INCLUDE, "-o", out or LIB]
+    cmd += ["-D" + d for d in defines] + sources()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)
     env.pop("CC", None)   # the image's CC wrapper is not meant for nvcc's host pass
     env.pop("CXX", None)
     subprocess.check_call(cmd, env=env)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

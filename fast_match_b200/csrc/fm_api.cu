@@ -3,7 +3,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "fm_common.cuh"
 
@@ -16,6 +18,34 @@ void set_error(const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+static std::atomic<long long> g_launches{0};
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<cudaEvent_t> g_prof_events;   // start/stop pairs
+static cudaEvent_t g_prof_open = nullptr;
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+void prof_begin(cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (!g_prof_on) return;
+    cudaEvent_t a;
+    if (cudaEventCreate(&a) != cudaSuccess) return;
+    cudaEventRecord(a, s);
+    g_prof_open = a;
+}
+
+void prof_end(cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (!g_prof_on || !g_prof_open) return;
+    cudaEvent_t b;
+    if (cudaEventCreate(&b) != cudaSuccess) return;
+    cudaEventRecord(b, s);
+    g_prof_events.push_back(g_prof_open);
+    g_prof_events.push_back(b);
+    g_prof_open = nullptr;
 }
 
 namespace {
@@ -91,6 +121,34 @@ extern "C" {
 
 int fm_version(void) { return 100; }
 
+long long fm_launch_count(void) { return fm::g_launches.load(); }
+
+int fm_profile_enable(int on) {
+    std::lock_guard<std::mutex> lock(fm::g_prof_mu);
+    fm::g_prof_on = on != 0;
+    return FM_OK;
+}
+
+int fm_profile_read(double *total_ms, int *launches, int reset) {
+    std::lock_guard<std::mutex> lock(fm::g_prof_mu);
+    double tot = 0;
+    int n = 0;
+    for (size_t i = 0; i + 1 < fm::g_prof_events.size(); i += 2) {
+        float ms = 0;
+        FM_CUDA_TRY(cudaEventSynchronize(fm::g_prof_events[i + 1]));
+        FM_CUDA_TRY(cudaEventElapsedTime(&ms, fm::g_prof_events[i], fm::g_prof_events[i + 1]));
+        tot += ms;
+        ++n;
+    }
+    if (reset) {
+        for (cudaEvent_t e : fm::g_prof_events) cudaEventDestroy(e);
+        fm::g_prof_events.clear();
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = n;
+    return FM_OK;
+}
+
 const char *fm_last_error(void) { return fm::g_err; }
 
 int fm_device_caps(int device, int *sm_major, int *sm_minor, int *sm_count, int *has_tcgen05) {
@@ -162,6 +220,7 @@ int fm_ratio_f32sqrt(const uint32_t *num_d2, int64_t num_stride, const uint32_t 
                                                                den_stride, den_f32, M, tau, ratio,
                                                                mask);
     FM_CUDA_TRY(cudaGetLastError());
+    fm::count_launch();
     return FM_OK;
 }
 
@@ -206,6 +265,7 @@ int fm_merge_top2(const uint64_t *keys, int32_t S, int64_t M, uint64_t *out_keys
     k_merge<<<grid_for(M, 256), 256, 0, (cudaStream_t)stream>>>(
         (const unsigned long long *)keys, S, M, (unsigned long long *)out_keys, d2, idx);
     FM_CUDA_TRY(cudaGetLastError());
+    fm::count_launch();
     return FM_OK;
 }
 
@@ -233,8 +293,15 @@ int ensure(uint8_t **p, size_t *cap, size_t need, bool pinned) {
 inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 }  // namespace
 
+static bool is_device_accessible_host(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 int fm_top2_host_u8(const uint8_t *q_host, int64_t M, const uint8_t *t_host, int64_t N,
-                    uint32_t *d2_host, int32_t *idx_host, float *dist_host, int device) {
+                    uint32_t *d2_host, int32_t *idx_host, float *dist_host, double tau,
+                    uint8_t *mask_host, int device) {
     if (M < 0 || N < 0 || (M > 0 && (!q_host || !d2_host || !idx_host)) || (N > 0 && !t_host)) {
         set_error("fm_top2_host_u8: bad argument");
         return FM_EINVAL;
@@ -251,33 +318,57 @@ int fm_top2_host_u8(const uint8_t *q_host, int64_t M, const uint8_t *t_host, int
     }
     const size_t qb = (size_t)M * FM_DIM, tb = (size_t)N * FM_DIM;
     const size_t ob_d2 = (size_t)M * 2 * 4, ob_idx = ob_d2, ob_dist = dist_host ? ob_d2 : 0;
+    const size_t ob_mask = mask_host ? (size_t)M : 0;
     const size_t wsb = fm_top2_workspace_bytes(M, N);
-    // device layout: q | t | d2 | idx | dist | ws
+    // device layout: q | t | d2 | idx | dist | mask | ws
     const size_t o_q = 0, o_t = up256(qb), o_d2 = o_t + up256(tb), o_idx = o_d2 + up256(ob_d2),
-                 o_dist = o_idx + up256(ob_idx), o_ws = o_dist + up256(ob_dist),
-                 total = o_ws + up256(wsb);
+                 o_dist = o_idx + up256(ob_idx), o_mask = o_dist + up256(ob_dist),
+                 o_ws = o_mask + up256(ob_mask), total = o_ws + up256(wsb);
     int rc;
     if ((rc = ensure(&c.dev, &c.dev_cap, total, false)) != FM_OK) return rc;
-    if ((rc = ensure(&c.pin_in, &c.pin_in_cap, o_d2, true)) != FM_OK) return rc;
-    if ((rc = ensure(&c.pin_out, &c.pin_out_cap, o_ws - o_d2, true)) != FM_OK) return rc;
-    memcpy(c.pin_in + o_q, q_host, qb);
-    if (tb) memcpy(c.pin_in + o_t, t_host, tb);
-    FM_CUDA_TRY(cudaMemcpyAsync(c.dev, c.pin_in, o_t + tb, cudaMemcpyHostToDevice, c.stream));
-    rc = fm_top2_u8(c.dev + o_q, M, c.dev + o_t, N, 0, (uint32_t *)(c.dev + o_d2),
-                    (int32_t *)(c.dev + o_idx), nullptr, c.dev + o_ws, up256(wsb), FM_ALGO_AUTO,
-                    c.stream);
+    // inputs: pinned / registered host memory is copied straight from the caller's buffer,
+    // pageable memory goes through the library's pinned staging area
+    const bool q_pinned = is_device_accessible_host(q_host);
+    const bool t_pinned = tb == 0 || is_device_accessible_host(t_host);
+    if (!q_pinned || !t_pinned) {
+        if ((rc = ensure(&c.pin_in, &c.pin_in_cap, o_d2, true)) != FM_OK) return rc;
+    }
+    const uint8_t *qsrc = q_host, *tsrc = t_host;
+    if (!q_pinned) { memcpy(c.pin_in + o_q, q_host, qb); qsrc = c.pin_in + o_q; }
+    if (!t_pinned && tb) { memcpy(c.pin_in + o_t, t_host, tb); tsrc = c.pin_in + o_t; }
+    FM_CUDA_TRY(cudaMemcpyAsync(c.dev + o_q, qsrc, qb, cudaMemcpyHostToDevice, c.stream));
+    if (tb) FM_CUDA_TRY(cudaMemcpyAsync(c.dev + o_t, tsrc, tb, cudaMemcpyHostToDevice, c.stream));
+    uint32_t *d2_dev = (uint32_t *)(c.dev + o_d2);
+    rc = fm_top2_u8(c.dev + o_q, M, c.dev + o_t, N, 0, d2_dev, (int32_t *)(c.dev + o_idx), nullptr,
+                    c.dev + o_ws, up256(wsb), FM_ALGO_AUTO, c.stream);
     if (rc != FM_OK) return rc;
     if (dist_host) {
-        k_dist<<<grid_for(M * 2, 256), 256, 0, c.stream>>>((const uint32_t *)(c.dev + o_d2),
-                                                          (float *)(c.dev + o_dist), M * 2);
+        k_dist<<<grid_for(M * 2, 256), 256, 0, c.stream>>>(d2_dev, (float *)(c.dev + o_dist), M * 2);
         FM_CUDA_TRY(cudaGetLastError());
+        fm::count_launch();
     }
-    FM_CUDA_TRY(cudaMemcpyAsync(c.pin_out, c.dev + o_d2, o_ws - o_d2, cudaMemcpyDeviceToHost,
-                                c.stream));
+    if (mask_host) {   // Lowe ratio test d1/d2 < tau, fused into the same call
+        rc = fm_ratio_f32sqrt(d2_dev, 2, d2_dev + 1, 2, nullptr, M, tau, nullptr, c.dev + o_mask, c.stream);
+        if (rc != FM_OK) return rc;
+    }
+    const bool out_pinned = is_device_accessible_host(d2_host) && is_device_accessible_host(idx_host) &&
+                            (!dist_host || is_device_accessible_host(dist_host)) &&
+                            (!mask_host || is_device_accessible_host(mask_host));
+    if (out_pinned) {
+        FM_CUDA_TRY(cudaMemcpyAsync(d2_host, c.dev + o_d2, ob_d2, cudaMemcpyDeviceToHost, c.stream));
+        FM_CUDA_TRY(cudaMemcpyAsync(idx_host, c.dev + o_idx, ob_idx, cudaMemcpyDeviceToHost, c.stream));
+        if (dist_host) FM_CUDA_TRY(cudaMemcpyAsync(dist_host, c.dev + o_dist, ob_dist, cudaMemcpyDeviceToHost, c.stream));
+        if (mask_host) FM_CUDA_TRY(cudaMemcpyAsync(mask_host, c.dev + o_mask, ob_mask, cudaMemcpyDeviceToHost, c.stream));
+        FM_CUDA_TRY(cudaStreamSynchronize(c.stream));
+        return FM_OK;
+    }
+    if ((rc = ensure(&c.pin_out, &c.pin_out_cap, o_ws - o_d2, true)) != FM_OK) return rc;
+    FM_CUDA_TRY(cudaMemcpyAsync(c.pin_out, c.dev + o_d2, o_ws - o_d2, cudaMemcpyDeviceToHost, c.stream));
     FM_CUDA_TRY(cudaStreamSynchronize(c.stream));
     memcpy(d2_host, c.pin_out, ob_d2);
     memcpy(idx_host, c.pin_out + (o_idx - o_d2), ob_idx);
     if (dist_host) memcpy(dist_host, c.pin_out + (o_dist - o_d2), ob_dist);
+    if (mask_host) memcpy(mask_host, c.pin_out + (o_mask - o_d2), ob_mask);
     return FM_OK;
 }
 

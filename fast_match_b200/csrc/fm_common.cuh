@@ -49,6 +49,14 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
     return __shfl_xor_sync(0xffffffffu, v, m);
 }
 
+// Instrumentation shared by the translation units (fm_api.cu owns the storage).
+//  * every kernel launch of the library is counted (fm_launch_count);
+//  * when profiling is on (fm_profile_enable) the dominant kernel of each call is bracketed by a
+//    CUDA event pair on the launching stream; fm_profile_read sums the elapsed times.
+void count_launch(int n = 1);
+void prof_begin(cudaStream_t s);   // no-op unless profiling is enabled
+void prof_end(cudaStream_t s);
+
 // launchers implemented in the kernel translation units
 int launch_sweep_mma_dense(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N,
                            int32_t t_index_base, uint32_t *d2, int32_t *idx, uint64_t *keys,

@@ -237,9 +237,12 @@ int launch_sweep_mma_dense(const uint8_t *q, int64_t M, const uint8_t *t, int64_
     if (M == 0) return FM_OK;
     int64_t slabs = (M + TM - 1) / TM;
     dim3 grid(1, (unsigned)(slabs < 65535 ? slabs : 65535));
+    prof_begin(s);
     k_sweep_mma<false><<<grid, NTHREADS, 0, s>>>(q, nullptr, nullptr, t, nullptr, nullptr, M, N,
                                                  t_index_base, d2, idx, keys, nullptr);
+    prof_end(s);
     FM_CUDA_TRY(cudaGetLastError());
+    count_launch();
     return FM_OK;
 }
 
@@ -254,11 +257,14 @@ int launch_sweep_mma_grouped(const uint8_t *qpool, const int32_t *q_gather, cons
     if (slabs < 1) slabs = 1;
     if (slabs > 64) slabs = 64;  // kernel loops over the remaining slabs
     dim3 grid((unsigned)G, (unsigned)slabs);
+    prof_begin(s);
     k_sweep_mma<true><<<grid, NTHREADS, 0, s>>>(qpool, q_gather, q_off, tpool, t_off, t_base, 0, 0, 0,
                                                 q2t_d2, q2t_idx, nullptr, colkeys);
+    prof_end(s);
     FM_CUDA_TRY(cudaGetLastError());
     k_grouped_finalize<<<G, 128, 0, s>>>(q_off, t_off, colkeys, q2t_idx, t2q_idx, mutual);
     FM_CUDA_TRY(cudaGetLastError());
+    count_launch(2);
     return FM_OK;
 }
 

@@ -61,7 +61,8 @@ constexpr int SMEM_AX = SMEM_A + SUBS * A_BYTES;
 constexpr int SMEM_B = SMEM_AX + AX_BYTES;
 constexpr int SMEM_KEYS = SMEM_B + STAGES * STAGE_BYTES;        // [256 rows][4 col quarters][2] u64
 constexpr int SMEM_M2 = SMEM_KEYS + SUBS * BM * 4 * 2 * 8;      // [256 rows] shared second-best bound
-constexpr int SMEM_BARS = SMEM_M2 + SUBS * BM * 4;
+constexpr int SMEM_CK = SMEM_M2 + SUBS * BM * 4;                // [16 warps][2 slots][64] exact-key constants
+constexpr int SMEM_BARS = SMEM_CK + EPI_WARPS * 2 * COLS_PER_WARP * 4;
 constexpr int SMEM_TOTAL = SMEM_BARS + (int)sizeof(Bars);
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;                   // slack for 1024-B alignment
 
@@ -123,6 +124,11 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -258,6 +264,15 @@ __global__ void k_target_aux(const int *__restrict__ tn, const int *__restrict__
 // ---------------------------------------------------------------------------------------------
 // main kernel
 // ---------------------------------------------------------------------------------------------
+#ifdef FM_TC_PROF
+__device__ unsigned long long g_prof[16];
+#define PROF_T0() const long long _t0 = clock64()
+#define PROF_ADD(slot) _pacc[slot] += (unsigned long long)(clock64() - _t0)
+#else
+#define PROF_T0()
+#define PROF_ADD(slot)
+#endif
+
 struct RowState {
     int m1, i1, m2, i2;   // best / second-best partial distance (|t|^2 - 2 q.t) and target index
 };
@@ -275,13 +290,12 @@ __device__ __forceinline__ int max16(const int *v) {
 // key = partial * 256 + column (unique inside a tile, so integer order on keys is the
 // lexicographic (distance, index) order).  `bound` <= s.m2, so a key below it enters the top-2;
 // the chunk's runner-up only matters when the chunk also produced a new best.
-__device__ __forceinline__ void slow16(const int *v, const int *__restrict__ ckey, int jtile,
-                                       int bound, RowState &s) {
+__device__ __forceinline__ void slow16(const int *v, const int4 *cp, int jtile, int bound,
+                                       RowState &s) {
     int k[16];
-    const int4 *cp = (const int4 *)ckey;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int4 c = __ldg(cp + i);
+        const int4 c = cp[i];
         k[4 * i + 0] = c.x - 512 * v[4 * i + 0];
         k[4 * i + 1] = c.y - 512 * v[4 * i + 1];
         k[4 * i + 2] = c.z - 512 * v[4 * i + 2];
@@ -321,6 +335,10 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
           const int *__restrict__ cg_ptr, uint32_t *__restrict__ out_d2,
           int32_t *__restrict__ out_idx, unsigned long long *__restrict__ out_keys,
           unsigned long long *__restrict__ partial) {
+#ifdef FM_TC_PROF
+    const long long _tk0 = clock64();
+    unsigned long long _pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     Bars *bars = (Bars *)(smem + SMEM_BARS);
@@ -364,7 +382,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
             for (int it = 0; it < ntiles; ++it) {
                 const int stage = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1);
+                { PROF_T0(); mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1); PROF_ADD(2); }
                 const uint32_t fb = smem_u32(&bars->full[stage]);
                 mbar_expect_tx(fb, B_BYTES + BX_BYTES);
                 uint8_t *st = smem + SMEM_B + stage * STAGE_BYTES;
@@ -382,14 +400,14 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
             for (int it = 0; it < ntiles; ++it) {
                 const int stage = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(smem_u32(&bars->full[stage]), ph);
+                { PROF_T0(); mbar_wait(smem_u32(&bars->full[stage]), ph); PROF_ADD(0); }
                 tc_fence_after();
                 const uint32_t sb = smem_u32(smem + SMEM_B + stage * STAGE_BYTES);
                 const uint64_t bdesc = make_desc(sb);
                 const uint64_t bxdesc = make_desc_sw32(sb + B_BYTES);
 #pragma unroll
                 for (int s = 0; s < SUBS; ++s) {
-                    mbar_wait(smem_u32(&bars->tmem_empty[s]), (it & 1) ^ 1);
+                    { PROF_T0(); mbar_wait(smem_u32(&bars->tmem_empty[s]), (it & 1) ^ 1); PROF_ADD(1); }
                     tc_fence_after();
                     const uint64_t adesc = make_desc(smem_u32(smem + SMEM_A + s * A_BYTES));
 #pragma unroll
@@ -417,15 +435,33 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         }
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
 
+        // exact-key constants of this warp's 64 columns: warp-private, double-buffered in smem
+        int *ckbuf = (int *)(smem + SMEM_CK) + ew * 2 * COLS_PER_WARP;
+        const int *ckg = ckey + (int64_t)tile_begin * BN + cq * COLS_PER_WARP;
+        if (lane < 16 && ntiles > 0) cp_async16(smem_u32(ckbuf + lane * 4), ckg + lane * 4);
+        cp_async_commit();
+
         for (int it = 0; it < ntiles; ++it) {
             const int jtile = (tile_begin + it) * BN;
-            const int *ck = ckey + jtile + cq * COLS_PER_WARP;
+            if (lane < 16 && it + 1 < ntiles)
+                cp_async16(smem_u32(ckbuf + ((it + 1) & 1) * COLS_PER_WARP + lane * 4),
+                           ckg + (int64_t)(it + 1) * BN + lane * 4);
+            cp_async_commit();
+            cp_async_wait1();
+            __syncwarp();
+            const int4 *ck = (const int4 *)(ckbuf + (it & 1) * COLS_PER_WARP);
 #pragma unroll
             for (int s = 0; s < SUBS; ++s) {
                 // Bound shared by the 4 warps that sweep this row's other column quarters.  It is
                 // applied non-strictly (+1): a sibling's candidate may carry a higher index.
                 const int shared_m2 = sm2[s * BM + row_in_sub];
+#ifdef FM_TC_PROF
+                const long long _te0 = clock64();
+#endif
                 mbar_wait(smem_u32(&bars->tmem_full[s]), it & 1);
+#ifdef FM_TC_PROF
+                const long long _te1 = clock64();
+#endif
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + s * BN + cq * COLS_PER_WARP;
                 int v0[32], v1[32];
@@ -435,18 +471,32 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[s]));
-                const int m2_before = st[s].m2;
+#ifdef FM_TC_PROF
+                const long long _te2 = clock64();
+#endif
                 int bound = min(st[s].m2, shared_m2 + 1);
                 int thr = (cg - bound) >> 1;        // acc' > thr  <=>  C - 2 acc' < bound
-#define FM_CHUNK(V, COL)                                                        \
-                if (max16(V + ((COL) & 31)) > thr) {                               \
-                    slow16(V + ((COL) & 31), ck + (COL), jtile, bound, st[s]);     \
-                    bound = min(st[s].m2, shared_m2 + 1);                          \
-                    thr = (cg - bound) >> 1;                                       \
+#define FM_CHUNK(V, COL)                                                                  \
+                if (max16(V) > thr) {                                                        \
+                    const int m2_before = st[s].m2;                                          \
+                    slow16(V, ck + (COL) / 4, jtile, bound, st[s]);                          \
+                    if (st[s].m2 < m2_before) {                                              \
+                        atomicMin(&sm2[s * BM + row_in_sub], st[s].m2);                      \
+                        bound = min(st[s].m2, bound);                                        \
+                        thr = (cg - bound) >> 1;                                             \
+                    }                                                                        \
                 }
-                FM_CHUNK(v0, 0) FM_CHUNK(v0, 16) FM_CHUNK(v1, 32) FM_CHUNK(v1, 48)
+                FM_CHUNK(v0, 0) FM_CHUNK(v0 + 16, 16) FM_CHUNK(v1, 32) FM_CHUNK(v1 + 16, 48)
 #undef FM_CHUNK
-                if (st[s].m2 < m2_before) atomicMin(&sm2[s * BM + row_in_sub], st[s].m2);
+#ifdef FM_TC_PROF
+                if (lane == 0) {
+                    const long long _te3 = clock64();
+                    _pacc[4] += (unsigned long long)(_te1 - _te0);   // wait tmem_full
+                    _pacc[5] += (unsigned long long)(_te2 - _te1);   // tmem load
+                    _pacc[6] += (unsigned long long)(_te3 - _te2);   // filter + updates
+                    _pacc[7] += 1ull;
+                }
+#endif
             }
         }
         // ---- merge the 4 column quarters of every row through shared memory
@@ -486,6 +536,11 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
 
     tc_fence_before();
     __syncthreads();
+#ifdef FM_TC_PROF
+    if ((threadIdx.x & 31) == 0)
+        for (int i = 0; i < 8; ++i) if (_pacc[i]) atomicAdd(&g_prof[i], _pacc[i]);
+    if (threadIdx.x == 0) { atomicAdd(&g_prof[8], (unsigned long long)(clock64() - _tk0)); atomicAdd(&g_prof[9], 1ull); atomicAdd(&g_prof[10], (unsigned long long)ntiles); }
+#endif
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
@@ -594,6 +649,15 @@ static Plan make_plan(int64_t M, int64_t N) {
 
 }  // namespace tc
 
+#ifdef FM_TC_PROF
+extern "C" int fm_debug_prof(unsigned long long *out16, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, tc::g_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tc::g_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 bool tc_supported() {
     static int ok = -1;
     if (ok < 0) {
@@ -640,6 +704,7 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     k_target_aux<<<(unsigned)((p.npad + 255) / 256), 256, 0, s>>>(tn, scal, N, p.npad, ckey,
                                                                  (uint4 *)digits, scal + 1);
     FM_CUDA_TRY(cudaGetLastError());
+    count_launch(3);
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -647,14 +712,18 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
         attr_set = true;
     }
     dim3 grid((unsigned)p.mblocks, (unsigned)p.splits);
+    prof_begin(s);
     k_top2_tc<<<grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base,
                                                  (int)p.ntiles, p.splits, qn, ckey, scal + 1, d2,
                                                  idx, (unsigned long long *)keys, partial);
+    prof_end(s);
     FM_CUDA_TRY(cudaGetLastError());
+    count_launch();
     if (partial) {
         k_merge_partial<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(partial, p.splits, M, d2, idx,
                                                                     (unsigned long long *)keys);
         FM_CUDA_TRY(cudaGetLastError());
+        count_launch();
     }
     return FM_OK;
 }

@@ -125,9 +125,23 @@ int fm_merge_top2(const uint64_t *keys, int32_t S, int64_t M, uint64_t *out_keys
  * caller holds numpy arrays.  Copies q/t to the device (pinned staging owned by
  * the library), runs fm_top2_u8, copies the result back and synchronises.
  * dist (nullable) [M][2] float32 = sqrtf((float)d2), i.e. DMatch.distance.
+ * mask (nullable) [M] uint8 = Lowe ratio test dist[i][0] / dist[i][1] < tau (Classic
+ * Matching.ipynb cell 3 JSON :65), computed on the device in the same call.
+ * Pinned / cudaHostRegister'ed caller buffers are used directly; pageable ones are staged.
  */
 int fm_top2_host_u8(const uint8_t *q_host, int64_t M, const uint8_t *t_host, int64_t N,
-                    uint32_t *d2_host, int32_t *idx_host, float *dist_host, int device);
+                    uint32_t *d2_host, int32_t *idx_host, float *dist_host, double tau,
+                    uint8_t *mask_host, int device);
+
+/*
+ * Instrumentation (no reference counterpart).  fm_launch_count: kernels launched by this
+ * library since load.  fm_profile_enable(1): bracket the dominant kernel of every following
+ * fm_top2_u8 / fm_grouped_mutual_u8 call with CUDA events on the launching stream;
+ * fm_profile_read sums their elapsed milliseconds (synchronises on the events).
+ */
+long long fm_launch_count(void);
+int fm_profile_enable(int on);
+int fm_profile_read(double *total_ms, int *launches, int reset);
 
 #ifdef __cplusplus
 }
