@@ -74,7 +74,7 @@ def match_thumbs(img, query_cache, thumb_x=400, thumb_y=400, features=matchutil.
     t_keypoints, t_descriptors = features(target)
     q_distances = query_cache.thumb["distances"]
     q_dev = query_cache.thumb["descriptors"]
-    t_dev = matchutil.to_device(t_descriptors, q_dev.device)
+    t_dev = _to_pool(matchutil.to_u8(t_descriptors), q_dev)
     qi, ti, dist = _mutual_pairs(q_dev, t_dev)
     with numpy.errstate(divide="ignore", invalid="ignore"):
         ratios = dist.astype(numpy.float64) / q_distances[qi]
@@ -101,6 +101,8 @@ class _Rounds(object):
         self.memo = {}
         self.cells = {}        # (col, row) -> (start row in pool, count, positions float64 [n,2])
         self.pool = None       # device uint8 [rows, 128]: descriptors of every fetched cell
+        self.visited = set()   # cells in first-visit order of the depth-first replay
+        self.last = None       # what Grid_Cache.last would be in a round-by-round run
         self.stats = stats if stats is not None else {}
         for k in ("waves", "rounds_evaluated", "launches"):
             self.stats.setdefault(k, 0)
@@ -113,7 +115,7 @@ class _Rounds(object):
         new = [c for c in wanted if c not in self.cells]
         if not new:
             return
-        dev = self.cache.original["descriptors"].device
+        like = self.cache.original["descriptors"]
         start = 0 if self.pool is None else self.pool.shape[0]
         chunks = []
         for (col, row) in new:
@@ -127,11 +129,9 @@ class _Rounds(object):
             start += len(u8)
             chunks.append(u8)
         flat = numpy.concatenate(chunks) if chunks else numpy.zeros((0, 128), numpy.uint8)
-        if len(flat):
-            up = torch.from_numpy(flat).to(dev)
-            self.pool = up if self.pool is None else torch.cat([self.pool, up])
-        elif self.pool is None:
-            self.pool = torch.zeros((0, 128), dtype=torch.uint8, device=dev)
+        if len(flat) or self.pool is None:
+            up = _to_pool(flat, like)
+            self.pool = up if self.pool is None else _pool_cat(self.pool, up)
 
     def evaluate(self, keys):
         """Run every round in `keys` (not yet memoised) as one grouped launch."""
@@ -157,6 +157,15 @@ class _Rounds(object):
         self.stats["waves"] += 1
         self.stats["launches"] += 1
         self.stats["rounds_evaluated"] += len(keys)
+
+
+def _to_pool(u8, like):
+    """Host u8 descriptors -> resident device rows next to `like`."""
+    return torch.from_numpy(numpy.ascontiguousarray(u8)).to(like.device)
+
+
+def _pool_cat(pool, rows):
+    return torch.cat([pool, rows])
 
 
 def _run_groups(q_dev, q_lists, t_pool, t_starts, t_counts):
@@ -198,7 +207,6 @@ def do_iter(seeds, rounds, tau, log=None):
     matches = []
     has_matched = set()
     found_matches = {}
-    visited_cells = set()
 
     def cell_key(item):
         query_pos, target_pos = item
@@ -228,11 +236,12 @@ def do_iter(seeds, rounds, tau, log=None):
                 wave.append(rounds.key(other[0], ok[0], ok[1]))
             rounds.evaluate(wave)
         result_pos, ratios, query_idx = rounds.memo[rk]
-        if (col, row) not in visited_cells:
+        if (col, row) not in rounds.visited:
             # Grid_Cache.last only moves when a cell is cached for the first time (cache.pyx:105);
             # cells are prefetched by waves here, so replay that bookkeeping in visit order.
-            visited_cells.add((col, row))
-            grid.last = grid.rect(col, row)
+            rounds.visited.add((col, row))
+            rounds.last = grid.rect(col, row)
+        grid.last = rounds.last
         accepted = ratios < tau
         acc_pos = result_pos[accepted]
         neighbors = get_neighbors(target_pos, acc_pos, grid)

@@ -1,0 +1,149 @@
+"""CPU: host-side logic of the drop-in layer (no GPU, no CUDA calls).
+
+The wave-batched flood fill (fast_match_b200/fastmatch.py) must emit exactly what the
+sequential round-by-round driver emits (oracle/fastmatch_ref.py, which restates
+fastmatch.pyx:56-180).  Here the two backend entry points of the product driver are replaced
+by oracle-backed stand-ins so that only the host logic is under test; the same comparison
+runs against the real CUDA backend in tests/test_gpu_fastmatch.py.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import fastmatch_ref
+from fast_match_b200 import cache as fm_cache
+from fast_match_b200 import fastmatch
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_grid_geometry_matches_reference_restatement():
+    rng = np.random.default_rng(0)
+    for (w, h, cw, ch, m) in [(800, 640, 50, 50, 25), (801, 637, 75, 60, 30), (120, 90, 50, 50, 10), (50, 50, 50, 50, 0)]:
+        img = np.zeros((h, w, 3), np.uint8)
+        a = fm_cache.Grid_Cache(img, (cw, ch), None, margin=m)
+        b = fastmatch_ref.RefGrid(img, (cw, ch), lambda c: c.shape, m)
+        assert (a.rows, a.cols) == (b.rows, b.cols)
+        for _ in range(300):
+            x, y = rng.uniform(0, w), rng.uniform(0, h)
+            assert a.block(x, y) == b.block(x, y)
+            assert tuple(a.offset(x, y)) == tuple(b.offset(x, y))
+            col, row = a.block(x, y)
+            assert np.array_equal(a.center(col, row), b.center(col, row))
+            px, py = rng.uniform(0, w), rng.uniform(0, h)
+            assert np.array_equal(a.get_neighbor(col, row, px, py), b.get_neighbor(col, row, px, py))
+            cell = a.get(x, y)
+            b.get(x, y)
+            assert a.last == b.last
+            (x0, x1), (y0, y1) = a.rect(col, row)
+            assert cell.shape[:2] == (min(y1, h) - y0, min(x1, w) - x0)   # numpy clips the crop, the logged rect is not clipped
+        with pytest.raises(Exception):
+            a.get(w + 1, 1)
+
+
+def _stub_backend(monkeypatch):
+    """Replace the two CUDA entry points used by the driver with oracle-backed stand-ins."""
+    def mutual_pairs(q, t):
+        return fastmatch_ref.oracle_mutual(np.asarray(q), np.asarray(t))
+
+    def run_groups(q, q_lists, t_pool, t_starts, t_counts):
+        q_off = np.concatenate([[0], np.cumsum([len(x) for x in q_lists])]).astype(np.int64)
+        t_off = np.concatenate([[0], np.cumsum(t_counts)]).astype(np.int64)
+        tp = np.concatenate([t_pool[s:s + c] for s, c in zip(t_starts, t_counts)] + [np.zeros((0, 128), np.uint8)])
+        gather = np.concatenate(list(q_lists) + [np.zeros(0, np.int64)]).astype(np.int32)
+        d2, idx, t2q = oracle.c_grouped_mutual(np.asarray(q), q_off, tp, t_off, q_gather=gather)
+        out = []
+        for g in range(len(q_lists)):
+            qs, ts = slice(q_off[g], q_off[g + 1]), slice(t_off[g], t_off[g + 1])
+            keep = oracle.mutual_pairs(idx[qs], t2q[ts])
+            out.append((keep, idx[qs][keep, 0].astype(np.int64), np.sqrt(d2[qs][keep, 0].astype(np.float32))))
+        return out
+    monkeypatch.setattr(fastmatch, "_mutual_pairs", mutual_pairs)
+    monkeypatch.setattr(fastmatch, "_run_groups", run_groups)
+    monkeypatch.setattr(fastmatch, "_to_pool", lambda u8, like: np.ascontiguousarray(u8))
+    monkeypatch.setattr(fastmatch, "_pool_cat", lambda a, b: np.concatenate([a, b]))
+
+
+def _same_matches(a, b):
+    assert len(a) == len(b)
+    for (ia, da), (ib, db) in zip(a, b):
+        assert int(ia) == int(ib)
+        assert np.array_equal(da["positions"], db["positions"]) and da["ratio"] == db["ratio"]
+
+
+def _same_logs(la, lb):
+    assert len(la) == len(lb)
+    for x, y in zip(la, lb):
+        assert set(x) == set(y) == {"query_pos", "target_pos", "target_grid", "matches", "radius", "ratios", "margin"}
+        assert np.array_equal(x["query_pos"], y["query_pos"]) and np.array_equal(x["target_pos"], y["target_pos"])
+        assert x["target_grid"] == y["target_grid"] and x["radius"] == y["radius"] and x["margin"] == y["margin"]
+        assert np.array_equal(x["matches"], y["matches"]) and np.array_equal(x["ratios"], y["ratios"])
+
+
+@pytest.fixture(scope="module")
+def graf():
+    import cv2
+    img1 = cv2.imread(os.path.join(GOLD, "graf1.png"))
+    cache = fastmatch_ref.RefMetricCache.from_image(os.path.join(GOLD, "graf4.png"))
+    return cache, img1
+
+
+@pytest.mark.parametrize("opts", [{}, {"grid_size": (75, 75), "grid_margin": 30, "radius": 50},
+                                  {"thumb_strategy": lambda t: t * 1.2, "radius": 60}])
+def test_wave_batched_flood_fill_equals_sequential(monkeypatch, graf, opts):
+    cache, img1 = graf
+    _stub_backend(monkeypatch)
+    for tau in (0.7, 0.9):
+        log_a, log_b, stats = [], [], {}
+        got = fastmatch.match(cache, img1, dict(opts, log=log_a, stats=stats))(tau)
+        ref = fastmatch_ref.match(cache, img1, dict(opts, log=log_b))
+        want = ref(tau)
+        _same_matches(got, want)
+        _same_logs(log_a, log_b)
+        assert stats["launches"] < max(ref.rounds, 2)          # rounds were batched into waves
+        assert stats["rounds_evaluated"] >= ref.rounds
+
+
+def test_readme_example_against_frozen_cv2_run(monkeypatch, graf):
+    """Config 1: Fast-Match graf img4 -> img1 at tau 0.7 / 0.9 equals the frozen run that used
+    cv2.BFMatcher as the matcher (valid when this box's SIFT reproduces the frozen descriptors)."""
+    cache, img1 = graf
+    gold = np.load(os.path.join(GOLD, "fastmatch_graf41.npz"))
+    h = gold["query_desc_hash"]
+    if (int(cache.original["descriptors"].astype(np.uint64).sum()), len(cache.original["descriptors"])) != (int(h[0]), int(h[1])):
+        pytest.skip("cv2 SIFT on this machine does not reproduce the frozen descriptors")
+    _stub_backend(monkeypatch)
+    for tau in (0.7, 0.9):
+        key = "tau%02d" % int(tau * 100)
+        log = []
+        ms = fastmatch.match(cache, img1, {"log": log})(tau)
+        assert np.array_equal(np.array([m[0] for m in ms], np.int64), gold[key + "_index"])
+        assert np.array_equal(np.array([m[1]["positions"] for m in ms]).reshape(-1, 2, 2), gold[key + "_pos"])
+        assert np.array_equal(np.array([m[1]["ratio"] for m in ms]), gold[key + "_ratio"])
+        assert len(log) == int(gold[key + "_rounds"][1])
+        assert np.array_equal(np.array([l["target_grid"] for l in log]).reshape(-1, 2, 2), gold[key + "_log_grid"])
+        assert np.array_equal(np.array([len(l["matches"]) for l in log]), gold[key + "_log_nmatch"])
+
+
+def test_matchlist_behaves_like_knnmatch_output():
+    from fast_match_b200 import matchutil
+    idx = np.array([[3, 1], [2, -1], [-1, -1]], np.int32)
+    d2 = np.array([[4, 9], [16, 0xFFFFFFFF], [0xFFFFFFFF, 0xFFFFFFFF]], np.int64)
+    ml = matchutil.MatchList(idx, d2, idx >= 0)
+    assert len(ml) == 3 and [len(m) for m in ml] == [2, 1, 0]
+    assert ml[0][1].trainIdx == 1 and ml[0][1].queryIdx == 0 and ml[0][1].distance == 3.0 and ml[0][0].imgIdx == 0
+    assert ml[-1] == [] and [m[0].distance for m in ml[:2]] == [2.0, 4.0]
+    with pytest.raises(ValueError):
+        matchutil.to_u8(np.full((2, 128), 0.5, np.float32))       # not integer valued: rejected, not rounded
+    assert matchutil.to_u8(None).shape == (0, 128)
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    from fast_match_b200 import backend, matchutil
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(backend.FastMatchError):
+        matchutil.bf_match(np.zeros((4, 128), np.uint8), np.zeros((4, 128), np.uint8), k=2)
