@@ -198,17 +198,28 @@ def siftlike_torch(lo, hi, seed, device):
 
 
 def plant_torch(q, t, t_lo, seed):
-    """Overwrite ~half of the target rows with noisy copies of pseudo-randomly chosen queries."""
+    """Overwrite ~half of the target rows with noisy copies of pseudo-randomly chosen queries.
+    Deterministic per 65536-row chunk of the *global* target index, so the data set does not
+    depend on how it is sharded."""
     import torch
-    g = torch.Generator(device=t.device)
-    g.manual_seed(seed * 7919 + t_lo)
+    chunk = 65536
     n = t.shape[0]
-    pick = torch.rand(n, generator=g, device=t.device) < 0.5
-    src = torch.randint(0, q.shape[0], (n,), generator=g, device=t.device)
-    sigma = torch.rand((n, 1), generator=g, device=t.device) * 36.0 + 4.0
-    noise = torch.randn((n, 128), generator=g, device=t.device) * sigma
-    planted = (q[src].float() + noise).round().clamp(0, 255).to(torch.uint8)
-    t[pick] = planted[pick]
+    pos = 0
+    while pos < n:
+        c = (t_lo + pos) // chunk
+        a = (t_lo + pos) - c * chunk
+        m = min(chunk - a, n - pos)
+        g = torch.Generator(device=t.device)
+        g.manual_seed(seed * 7919 + c)
+        pick = torch.rand(chunk, generator=g, device=t.device) < 0.5
+        src = torch.randint(0, q.shape[0], (chunk,), generator=g, device=t.device)
+        sigma = torch.rand((chunk, 1), generator=g, device=t.device) * 36.0 + 4.0
+        noise = torch.randn((chunk, 128), generator=g, device=t.device) * sigma
+        planted = (q[src].float() + noise).round().clamp(0, 255).to(torch.uint8)
+        view = t[pos:pos + m]
+        sel = pick[a:a + m]
+        view[sel] = planted[a:a + m][sel]
+        pos += m
     return t
 
 
