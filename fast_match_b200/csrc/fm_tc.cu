@@ -129,6 +129,22 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ int ld_shared_s32(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_shared_s32(uint32_t a, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ int4 ld_shared_v4(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void atom_shared_min_s32(uint32_t a, int v) {
+    asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -290,12 +306,12 @@ __device__ __forceinline__ int max16(const int *v) {
 // key = partial * 256 + column (unique inside a tile, so integer order on keys is the
 // lexicographic (distance, index) order).  `bound` <= s.m2, so a key below it enters the top-2;
 // the chunk's runner-up only matters when the chunk also produced a new best.
-__device__ __forceinline__ void slow16(const int *v, const int4 *cp, int jtile, int bound,
+__device__ __forceinline__ void slow16(const int *v, uint32_t ck_saddr, int jtile, int bound,
                                        RowState &s) {
     int k[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const int4 c = cp[i];
+        const int4 c = ld_shared_v4(ck_saddr + i * 16);
         k[4 * i + 0] = c.x - 512 * v[4 * i + 0];
         k[4 * i + 1] = c.y - 512 * v[4 * i + 1];
         k[4 * i + 2] = c.z - 512 * v[4 * i + 2];
@@ -427,61 +443,62 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         const int row_in_sub = lq * 32 + lane;
         const int cg = __ldg(cg_ptr);
         RowState st[SUBS];
-        int *sm2 = (int *)(smem + SMEM_M2);
+        // sm2[row]: (second-best partial distance + 1) published by the four warps that sweep the
+        // same row -- "+1" because a sibling's candidate may carry a higher index (non-strict).
+        const uint32_t sm2_a = smem_u32(smem + SMEM_M2) + row_in_sub * 4;
 #pragma unroll
         for (int s = 0; s < SUBS; ++s) {
             st[s].m1 = st[s].m2 = NONE_P; st[s].i1 = st[s].i2 = -1;
-            if (cq == 0) sm2[s * BM + row_in_sub] = NONE_P;
+            if (cq == 0) st_shared_s32(sm2_a + s * BM * 4, NONE_P);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
 
         // exact-key constants of this warp's 64 columns: warp-private, double-buffered in smem
-        int *ckbuf = (int *)(smem + SMEM_CK) + ew * 2 * COLS_PER_WARP;
-        const int *ckg = ckey + (int64_t)tile_begin * BN + cq * COLS_PER_WARP;
-        if (lane < 16 && ntiles > 0) cp_async16(smem_u32(ckbuf + lane * 4), ckg + lane * 4);
+        const uint32_t ck_a = smem_u32(smem + SMEM_CK) + ew * (2 * COLS_PER_WARP * 4);
+        const int *ckg = ckey + (int64_t)tile_begin * BN + cq * COLS_PER_WARP + lane * 4;
+        if (lane < 16 && ntiles > 0) cp_async16(ck_a + lane * 16, ckg);
         cp_async_commit();
+        // per-warp TMEM address of its 32 lanes x 64 columns (warp-uniform)
+        const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + cq * COLS_PER_WARP, 0);
+        const uint32_t full_a = smem_u32(&bars->tmem_full[0]), empty_a = smem_u32(&bars->tmem_empty[0]);
 
         for (int it = 0; it < ntiles; ++it) {
             const int jtile = (tile_begin + it) * BN;
             if (lane < 16 && it + 1 < ntiles)
-                cp_async16(smem_u32(ckbuf + ((it + 1) & 1) * COLS_PER_WARP + lane * 4),
-                           ckg + (int64_t)(it + 1) * BN + lane * 4);
+                cp_async16(ck_a + ((it + 1) & 1) * (COLS_PER_WARP * 4) + lane * 16, ckg + (int64_t)(it + 1) * BN);
             cp_async_commit();
             cp_async_wait1();
             __syncwarp();
-            const int4 *ck = (const int4 *)(ckbuf + (it & 1) * COLS_PER_WARP);
+            const uint32_t ck = ck_a + (it & 1) * (COLS_PER_WARP * 4);
 #pragma unroll
             for (int s = 0; s < SUBS; ++s) {
-                // Bound shared by the 4 warps that sweep this row's other column quarters.  It is
-                // applied non-strictly (+1): a sibling's candidate may carry a higher index.
-                const int shared_m2 = sm2[s * BM + row_in_sub];
+                const int shared_b = ld_shared_s32(sm2_a + s * BM * 4);
 #ifdef FM_TC_PROF
                 const long long _te0 = clock64();
 #endif
-                mbar_wait(smem_u32(&bars->tmem_full[s]), it & 1);
+                mbar_wait(full_a + s * 8, it & 1);
 #ifdef FM_TC_PROF
                 const long long _te1 = clock64();
 #endif
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + s * BN + cq * COLS_PER_WARP;
                 int v0[32], v1[32];
-                tmem_ld32(taddr, v0);
-                tmem_ld32(taddr + 32, v1);
+                tmem_ld32(taddr0 + s * BN, v0);
+                tmem_ld32(taddr0 + s * BN + 32, v1);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[s]));
+                if (lane == 0) mbar_arrive(empty_a + s * 8);
 #ifdef FM_TC_PROF
                 const long long _te2 = clock64();
 #endif
-                int bound = min(st[s].m2, shared_m2 + 1);
+                int bound = min(st[s].m2, shared_b);
                 int thr = (cg - bound) >> 1;        // acc' > thr  <=>  C - 2 acc' < bound
 #define FM_CHUNK(V, COL)                                                                  \
                 if (max16(V) > thr) {                                                        \
                     const int m2_before = st[s].m2;                                          \
-                    slow16(V, ck + (COL) / 4, jtile, bound, st[s]);                          \
+                    slow16(V, ck + (COL) * 4, jtile, bound, st[s]);                          \
                     if (st[s].m2 < m2_before) {                                              \
-                        atomicMin(&sm2[s * BM + row_in_sub], st[s].m2);                      \
+                        atom_shared_min_s32(sm2_a + s * BM * 4, st[s].m2 + 1);               \
                         bound = min(st[s].m2, bound);                                        \
                         thr = (cg - bound) >> 1;                                             \
                     }                                                                        \
