@@ -218,50 +218,43 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
 // ---------------------------------------------------------------------------------------------
-// pre-pass
+// pre-pass (one launch): |q_i|^2 for the queries; for every target j the norm digits and the
+// exact-key constant.
+//   E_j = 2*ceil(max(C - |t_j|^2, 0)/4)  with the fixed constant C = 2*EMAX, written as 16
+//   base-255 digits duplicated into both 16-byte halves of a 32-byte row (so the operand is
+//   indifferent to the 32B swizzle).  2 E_j >= C - |t_j|^2 always (targets with |t_j|^2 > C,
+//   i.e. mean byte value > 174, just get E_j = 0: the filter stays conservative, never wrong).
+//   ckey_j = (|t_j|^2 + 2 E_j) * 256 + (j & 255)  (wrapping int32; INT_MAX on the tile padding).
 // ---------------------------------------------------------------------------------------------
-// squared norms of 128-byte rows; optional global minimum
-__global__ void k_norms(const uint8_t *__restrict__ rows, int64_t n, int *__restrict__ out,
-                        int *__restrict__ gmin) {
+constexpr int EHALF_MAX = 255 * 255 * 15 + 254;   // digits 0..14 weigh 255, digit 15 weighs 1
+constexpr int EMAX = 2 * EHALF_MAX;
+constexpr int CG = 2 * EMAX;                      // the constant C of the filter
+__global__ void k_prepass(const uint8_t *__restrict__ q, int64_t M, const uint8_t *__restrict__ t,
+                          int64_t N, int64_t n_padded, int *__restrict__ qn,
+                          int *__restrict__ ckey, uint4 *__restrict__ digits) {
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t row = gt >> 3;
+    const int64_t row = gt >> 3;                  // 8 threads (16 B each) per descriptor
     const int sub = (int)(gt & 7);
+    const bool is_q = row < M;
+    const int64_t j = row - M;
+    const bool live = is_q || j < N;
     unsigned s = 0;
-    if (row < n) {
-        const uint4 x = *(const uint4 *)(rows + row * FM_DIM + sub * 16);
+    if (live) {
+        const uint8_t *src = is_q ? q + row * FM_DIM : t + j * FM_DIM;
+        const uint4 x = *(const uint4 *)(src + sub * 16);
         s = __dp4a(x.x, x.x, s); s = __dp4a(x.y, x.y, s);
         s = __dp4a(x.z, x.z, s); s = __dp4a(x.w, x.w, s);
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (sub == 0 && row < n) out[row] = (int)s;
-    if (gmin) {
-        int mn = row < n ? (int)s : I32_MAX;
-        for (int m = 16; m >= 1; m >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, m));
-        if ((threadIdx.x & 31) == 0 && mn != I32_MAX) atomicMin(gmin, mn);
-    }
-}
-
-// Per target j: E_j = 2*ceil(max(C - tn_j, 0)/4) <= EMAX with C = gmin + 2*EMAX, written as 16
-// base-255 digits duplicated into both 16-byte halves of a 32-byte row (so the operand is
-// indifferent to the 32B swizzle), and the exact-key constant
-// ckey_j = (tn_j + 2 E_j) * 256 + (j & 255)  (wrapping int32; INT_MAX on the tile padding).
-constexpr int EHALF_MAX = 255 * 255 * 15 + 254;   // digits 0..14 weigh 255, digit 15 weighs 1
-constexpr int EMAX = 2 * EHALF_MAX;
-__global__ void k_target_aux(const int *__restrict__ tn, const int *__restrict__ gmin, int64_t n,
-                             int64_t n_padded, int *__restrict__ ckey, uint4 *__restrict__ digits,
-                             int *__restrict__ cg_out) {
-    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int cg = *gmin + 2 * EMAX;
-    if (j == 0) *cg_out = cg;
-    if (j >= n_padded) return;
-    if (j >= n) { ckey[j] = I32_MAX; return; }
-    const int t = tn[j];
-    const int e = cg - t;
-    int half = e > 0 ? (e + 3) >> 2 : 0;          // E_j / 2
-    if (half > EHALF_MAX) half = EHALF_MAX;        // cannot happen (e <= 2*EMAX), kept as a guard
-    ckey[j] = (int)(((unsigned)(t + 4 * half) << 8) | (unsigned)(j & 255));
+    if (is_q) { if (sub == 0) qn[row] = (int)s; return; }
+    if (j >= n_padded || sub > 1) return;
+    if (j >= N) { if (sub == 0) ckey[j] = I32_MAX; return; }
+    const int tn = (int)s;
+    const int e = CG - tn;
+    const int half = e > 0 ? (e + 3) >> 2 : 0;    // E_j / 2  (<= EHALF_MAX because e <= 2*EMAX)
+    if (sub == 0) ckey[j] = (int)(((unsigned)(tn + 4 * half) << 8) | (unsigned)(j & 255));
     int sdig = half / 255;
     const unsigned r = (unsigned)(half - sdig * 255);
     unsigned w[4] = {0, 0, 0, 0};
@@ -272,9 +265,7 @@ __global__ void k_target_aux(const int *__restrict__ tn, const int *__restrict__
         w[k >> 2] |= (unsigned)d << (8 * (k & 3));
     }
     w[3] |= r << 24;
-    const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
-    digits[2 * j] = v;
-    digits[2 * j + 1] = v;
+    digits[2 * j + sub] = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -348,7 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
           const __grid_constant__ CUtensorMap map_x, int64_t M, int64_t N, int32_t t_index_base,
           int ntiles_total, int splits, const int *__restrict__ qn, const int *__restrict__ ckey,
-          const int *__restrict__ cg_ptr, uint32_t *__restrict__ out_d2,
+          uint32_t *__restrict__ out_d2,
           int32_t *__restrict__ out_idx, unsigned long long *__restrict__ out_keys,
           unsigned long long *__restrict__ partial) {
 #ifdef FM_TC_PROF
@@ -441,7 +432,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         const int lq = warp & 3;             // TMEM lane quarter this warp may touch
         const int cq = ew >> 2;              // column quarter
         const int row_in_sub = lq * 32 + lane;
-        const int cg = __ldg(cg_ptr);
+        constexpr int cg = CG;
         RowState st[SUBS];
         // sm2[row]: (second-best partial distance + 1) published by the four warps that sweep the
         // same row -- "+1" because a sibling's candidate may carry a higher index (non-strict).
@@ -704,8 +695,7 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     const Plan p = make_plan(M, N);
     if (ws_bytes < p.total) { set_error("tcgen05 path: workspace too small"); return FM_ENOSPACE; }
     uint8_t *w = (uint8_t *)ws;
-    int *tn = (int *)(w + p.off_tn), *ckey = (int *)(w + p.off_ckey), *qn = (int *)(w + p.off_qn);
-    int *scal = (int *)(w + p.off_scal);
+    int *ckey = (int *)(w + p.off_ckey), *qn = (int *)(w + p.off_qn);
     uint8_t *digits = w + p.off_digits;
     unsigned long long *partial = p.splits > 1 ? (unsigned long long *)(w + p.off_partial) : nullptr;
 
@@ -715,13 +705,10 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     if ((rc = make_map(&map_t, t, N, FM_DIM, BN, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
     if ((rc = make_map(&map_x, digits, N, 32, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) != FM_OK) return rc;
 
-    FM_CUDA_TRY(cudaMemsetAsync(scal, 0x7F, 8, s));
-    k_norms<<<(unsigned)((N * 8 + 255) / 256), 256, 0, s>>>(t, N, tn, scal);
-    k_norms<<<(unsigned)((M * 8 + 255) / 256), 256, 0, s>>>(q, M, qn, nullptr);
-    k_target_aux<<<(unsigned)((p.npad + 255) / 256), 256, 0, s>>>(tn, scal, N, p.npad, ckey,
-                                                                 (uint4 *)digits, scal + 1);
+    k_prepass<<<(unsigned)(((M + p.npad) * 8 + 255) / 256), 256, 0, s>>>(q, M, t, N, p.npad, qn, ckey,
+                                                                         (uint4 *)digits);
     FM_CUDA_TRY(cudaGetLastError());
-    count_launch(3);
+    count_launch();
 
     static bool attr_set = false;
     if (!attr_set) {
@@ -731,7 +718,7 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     dim3 grid((unsigned)p.mblocks, (unsigned)p.splits);
     prof_begin(s);
     k_top2_tc<<<grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base,
-                                                 (int)p.ntiles, p.splits, qn, ckey, scal + 1, d2,
+                                                 (int)p.ntiles, p.splits, qn, ckey, d2,
                                                  idx, (unsigned long long *)keys, partial);
     prof_end(s);
     FM_CUDA_TRY(cudaGetLastError());
