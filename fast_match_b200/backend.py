@@ -38,10 +38,10 @@ def lib():
         L.fm_top2_workspace_bytes.restype = sz
         L.fm_top2_u8.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, vp, sz, ctypes.c_int, vp]
         L.fm_ratio_f32sqrt.argtypes = [vp, i64, vp, i64, vp, i64, ctypes.c_double, vp, vp, vp]
-        L.fm_grouped_workspace_bytes.argtypes = [i64, i64, i32]
+        L.fm_grouped_workspace_bytes.argtypes = [i64, i64, i64, i32]
         L.fm_grouped_workspace_bytes.restype = sz
-        L.fm_grouped_mutual_u8.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i64, i32, vp, vp, vp, vp,
-                                           vp, sz, vp]
+        L.fm_grouped_mutual_u8.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, i64, i64, i32, vp, vp, vp,
+                                           vp, vp, sz, ctypes.c_int, vp]
         L.fm_merge_top2.argtypes = [vp, i32, i64, vp, vp, vp, vp]
         L.fm_top2_host_u8.argtypes = [vp, i64, vp, i64, vp, vp, vp, ctypes.c_double, vp, ctypes.c_int]
         L.fm_launch_count.restype = ctypes.c_longlong
@@ -138,7 +138,7 @@ def ratio(num_d2, den_d2=None, den_f32=None, tau=0.7, want_ratio=True):
 
 
 def grouped_mutual(qpool, q_off, tpool, t_off, q_gather=None, t_base=None, max_nq=None, total_q=None,
-                   total_t=None, want_mutual=True):
+                   total_t=None, want_mutual=True, algo=FM_ALGO_AUTO):
     """G independent mutual-NN rounds in one launch (see fm_grouped_mutual_u8)."""
     qpool, tpool = _desc(qpool, "qpool"), _desc(tpool, "tpool")
     dev = qpool.device
@@ -161,11 +161,12 @@ def grouped_mutual(qpool, q_off, tpool, t_off, q_gather=None, t_base=None, max_n
     t2q = torch.empty(total_t, dtype=torch.int32, device=dev)
     mutual = torch.empty(total_q, dtype=torch.uint8, device=dev) if want_mutual else None
     L = lib()
-    ws = _workspace(dev, L.fm_grouped_workspace_bytes(total_q, total_t, G))
+    tpool_rows = tpool.shape[0]
+    ws = _workspace(dev, L.fm_grouped_workspace_bytes(total_q, total_t, tpool_rows, G))
     with torch.cuda.device(dev):
         _check(L.fm_grouped_mutual_u8(_ptr(qpool), _ptr(q_gather), _ptr(q_off), _ptr(tpool),
-                                      _ptr(t_off), _ptr(t_base), G, total_q, total_t, int(max_nq), _ptr(d2),
-                                      _ptr(idx), _ptr(t2q), _ptr(mutual), _ptr(ws), ws.numel(),
+                                      _ptr(t_off), _ptr(t_base), G, total_q, total_t, tpool_rows, int(max_nq), _ptr(d2),
+                                      _ptr(idx), _ptr(t2q), _ptr(mutual), _ptr(ws), ws.numel(), int(algo),
                                       _stream(dev)), "fm_grouped_mutual_u8")
     return d2, idx, t2q, (mutual.bool() if want_mutual else None)
 

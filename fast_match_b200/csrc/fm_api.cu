@@ -224,32 +224,59 @@ int fm_ratio_f32sqrt(const uint32_t *num_d2, int64_t num_stride, const uint32_t 
     return FM_OK;
 }
 
-size_t fm_grouped_workspace_bytes(int64_t total_q, int64_t total_t, int32_t G) {
-    (void)total_q; (void)G;
-    return (size_t)(total_t > 0 ? total_t : 0) * sizeof(unsigned long long) + 16;
+size_t fm_grouped_workspace_bytes(int64_t total_q, int64_t total_t, int64_t tpool_rows, int32_t G) {
+    (void)G;
+    const size_t a = (size_t)(total_t > 0 ? total_t : 0) * sizeof(unsigned long long) + 16;
+    const size_t b = fm::grouped_tc_workspace_bytes(total_q > 0 ? total_q : 0,
+                                                    tpool_rows > 0 ? tpool_rows : 0, true);
+    return a > b ? a : b;
 }
 
 int fm_grouped_mutual_u8(const uint8_t *qpool, const int32_t *q_gather, const int64_t *q_off,
                          const uint8_t *tpool, const int64_t *t_off, const int64_t *t_base,
-                         int32_t G, int64_t total_q,
-                         int64_t total_t, int32_t max_nq, uint32_t *q2t_d2, int32_t *q2t_idx,
-                         int32_t *t2q_idx, uint8_t *mutual, void *ws, size_t ws_bytes,
-                         void *stream) {
-    if (G < 0 || total_q < 0 || total_t < 0 || max_nq < 0 || (G > 0 && (!q_off || !t_off)) ||
-        (total_q > 0 && (!qpool || !q2t_d2 || !q2t_idx)) || (total_t > 0 && (!tpool || !t2q_idx))) {
+                         int32_t G, int64_t total_q, int64_t total_t, int64_t tpool_rows,
+                         int32_t max_nq, uint32_t *q2t_d2, int32_t *q2t_idx, int32_t *t2q_idx,
+                         uint8_t *mutual, void *ws, size_t ws_bytes, int algo, void *stream) {
+    if (G < 0 || total_q < 0 || total_t < 0 || max_nq < 0 || tpool_rows < 0 ||
+        (G > 0 && (!q_off || !t_off)) || (total_q > 0 && (!qpool || !q2t_d2 || !q2t_idx)) ||
+        (total_t > 0 && (!tpool || !t2q_idx))) {
         set_error("fm_grouped_mutual_u8: bad argument");
         return FM_EINVAL;
     }
+    if (!t_base) tpool_rows = total_t;
     if (!aligned16(qpool) || !aligned16(tpool)) {
         set_error("fm_grouped_mutual_u8: descriptor pointers must be 16-byte aligned");
         return FM_EINVAL;
     }
-    if (ws_bytes < fm_grouped_workspace_bytes(total_q, total_t, G) || !ws) {
+    if (total_q > 0x7FFFFFFFll || tpool_rows > 0x7FFFFFFFll) {
+        set_error("fm_grouped_mutual_u8: row counts exceed int32");
+        return FM_EINVAL;
+    }
+    if (ws_bytes < fm_grouped_workspace_bytes(total_q, total_t, tpool_rows, G) || !ws) {
         set_error("fm_grouped_mutual_u8: workspace too small (%zu < %zu)", ws_bytes,
-                  fm_grouped_workspace_bytes(total_q, total_t, G));
+                  fm_grouped_workspace_bytes(total_q, total_t, tpool_rows, G));
         return FM_ENOSPACE;
     }
     if (G == 0) return FM_OK;
+    bool use_tc;
+    if (algo == FM_ALGO_TCGEN05) {
+        if (!fm::tc_supported()) {
+            set_error("fm_grouped_mutual_u8: FM_ALGO_TCGEN05 requested but the device is not sm_100");
+            return FM_EUNSUPPORTED;
+        }
+        use_tc = true;
+    } else if (algo == FM_ALGO_MMA_SYNC) {
+        use_tc = false;
+    } else if (algo == FM_ALGO_AUTO) {
+        use_tc = fm::tc_supported();
+    } else {
+        set_error("fm_grouped_mutual_u8: unknown algo %d", algo);
+        return FM_EINVAL;
+    }
+    if (use_tc)
+        return fm::launch_grouped_tc(qpool, q_gather, q_off, tpool, t_off, t_base, G, total_q, total_t,
+                                     tpool_rows, q2t_d2, q2t_idx, t2q_idx, mutual, ws, ws_bytes,
+                                     (cudaStream_t)stream);
     return fm::launch_sweep_mma_grouped(qpool, q_gather, q_off, tpool, t_off, t_base, G, total_q, total_t,
                                         max_nq, q2t_d2, q2t_idx, t2q_idx, mutual,
                                         (unsigned long long *)ws, (cudaStream_t)stream);

@@ -70,6 +70,12 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
                    uint32_t *d2, int32_t *idx, uint64_t *keys, void *ws, size_t ws_bytes,
                    cudaStream_t s);
 size_t top2_tc_workspace_bytes(int64_t M, int64_t N);
+size_t grouped_tc_workspace_bytes(int64_t total_q, int64_t tpool_rows, bool gather);
+int launch_grouped_tc(const uint8_t *qpool, const int32_t *q_gather, const int64_t *q_off,
+                      const uint8_t *tpool, const int64_t *t_off, const int64_t *t_base, int32_t G,
+                      int64_t total_q, int64_t total_t, int64_t tpool_rows, uint32_t *q2t_d2,
+                      int32_t *q2t_idx, int32_t *t2q_idx, uint8_t *mutual, void *ws, size_t ws_bytes,
+                      cudaStream_t s);
 bool tc_supported();
 
 }  // namespace fm

@@ -1,0 +1,390 @@
+// fm_grouped_tc.cu -- thousands of small mutual-nearest-neighbour rounds in ONE launch on the
+// tcgen05 tensor cores (sm_100a).
+//
+// Replaces the per-round cv2.BFMatcher(NORM_L2, crossCheck=True).knnMatch(query_ds, target_ds, k=1)
+// of fastmatch.pyx:161-162 (match_position, one call per flood-fill round) and :122-123
+// (match_thumbs).  A round is tiny (tens to hundreds of descriptors per side), so the path is
+// launch- and HBM-bound: every descriptor is read once (TMA, 32-row boxes = only the rows a round
+// needs), the distance tile lives in TMEM, and only (d2, index) pairs go back to HBM.
+//
+// Persistent kernel, one CTA per SM; groups are claimed from a global counter (sizes vary 256x).
+// For a group with nq queries and nt targets the CTA runs two passes of "units"
+//   pass 0: A = 128-query slab, B = up to 256 targets  -> per query the two smallest (d2, idx)
+//   pass 1: A = 128-target slab, B = up to 256 queries -> per target the nearest query (crossCheck)
+// so both directions are a per-row reduction over columns (no cross-lane reductions, no atomics);
+// the second pass costs tensor time only, which this path has to spare.  Units flow through the
+// same three pipelines as the dense kernel: TMA ring (A 16 KB + B 32 KB per stage) -> single-thread
+// tcgen05.mma kind::i8 (M = 128, N = round_up(valid B rows, 16)) -> two ping-pong 256-column
+// TMEM accumulators -> 16 epilogue warps.  The epilogue forms exact integer keys
+//   key = (|b_j|^2 - 2 a_i.b_j) * 256 + column      (one IMAD; |b_j|^2*256+column comes from smem)
+// and keeps the running minimum (pass 1) or two minima (pass 0) per row; integer order on keys is
+// the lexicographic (distance, index) order, chunks are visited in increasing index with strict
+// "<", so ties go to the lowest local index exactly as cv::batchDistance does.
+#include <cuda.h>
+
+#include "fm_common.cuh"
+#include "fm_tc_ptx.cuh"
+
+namespace fm {
+
+namespace gtc {
+
+using namespace tc;
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int STAGES = 3;
+constexpr int EPI_WARPS = 16;
+constexpr int NTHREADS = 128 + EPI_WARPS * 32;
+constexpr int COLS_PER_WARP = BN / 4;
+constexpr int A_BYTES = BM * FM_DIM, B_BYTES = BN * FM_DIM, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BOX_ROWS = 32, BOX_BYTES = BOX_ROWS * FM_DIM;
+constexpr int RING = 8;
+constexpr int I32_MAX = 0x7FFFFFFF;
+constexpr int NONE_P = 0x7FFFFF;
+
+enum { F_PASS1 = 1, F_FIRST = 2, F_LAST = 4, F_STOP = 8 };
+
+struct __align__(16) Slot {
+    int a_row0, a_valid, b_row0, b_valid, a_out0, b_local0, flags, n_mma;
+    int ck[BN];            // |b_c|^2 * 256 + c for the unit's B rows (INT_MAX beyond b_valid)
+};
+
+struct __align__(8) Bars {
+    unsigned long long full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    uint32_t tmem_base, pad;
+};
+
+constexpr int SMEM_STAGES = 0;
+constexpr int SMEM_RING = SMEM_STAGES + STAGES * STAGE_BYTES;
+constexpr int SMEM_KEYS = SMEM_RING + RING * (int)sizeof(Slot);       // [128 rows][4][2] u64
+constexpr int SMEM_BARS = SMEM_KEYS + BM * 4 * 2 * 8;
+constexpr int SMEM_TOTAL = SMEM_BARS + (int)sizeof(Bars);
+constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
+
+struct Params {
+    const int64_t *q_off, *t_off, *t_base;   // t_base nullable
+    const int *qnorm, *tnorm;                // per row of the (packed) query rows / target pool
+    int32_t G;
+    int *counter;
+    uint32_t *q2t_d2;
+    int32_t *q2t_idx, *t2q_idx;
+};
+
+__device__ __forceinline__ void insert2_key(int k, int &k1, int &k2) {
+    k2 = max(k1, min(k2, k));   // second smallest of {k1, k2, k}
+    k1 = min(k1, k);
+}
+
+// gather + norms: packed query rows (only when q_gather is given) and squared norms
+__global__ void k_pack_norms(const uint8_t *__restrict__ pool, const int32_t *__restrict__ gather,
+                             int64_t n, uint8_t *__restrict__ packed, int *__restrict__ norms) {
+    const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t row = gt >> 3;
+    const int sub = (int)(gt & 7);
+    unsigned s = 0;
+    if (row < n) {
+        const int64_t src = gather ? (int64_t)gather[row] : row;
+        const uint4 x = *(const uint4 *)(pool + src * FM_DIM + sub * 16);
+        if (packed) *(uint4 *)(packed + row * FM_DIM + sub * 16) = x;
+        s = __dp4a(x.x, x.x, s); s = __dp4a(x.y, x.y, s);
+        s = __dp4a(x.z, x.z, s); s = __dp4a(x.w, x.w, s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (sub == 0 && row < n) norms[row] = (int)s;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
+             const Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    Bars *bars = (Bars *)(smem + SMEM_BARS);
+    Slot *ring = (Slot *)(smem + SMEM_RING);
+    unsigned long long *skeys = (unsigned long long *)(smem + SMEM_KEYS);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_WARPS); }
+        fence_barrier_init();
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_t);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== producer: claims groups, emits units =====================
+        int u = 0;
+        bool done = false;
+        while (!done) {
+            int g = 0;
+            if (lane == 0) g = atomicAdd(P.counter, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            const bool stop = g >= P.G;
+            int64_t q0 = 0, t0 = 0, tsrc = 0;
+            int nq = 0, nt = 0;
+            if (!stop) {
+                q0 = P.q_off[g]; nq = (int)(P.q_off[g + 1] - q0);
+                t0 = P.t_off[g]; nt = (int)(P.t_off[g + 1] - t0);
+                tsrc = P.t_base ? P.t_base[g] : t0;
+            }
+            const int npass = (stop || nq == 0 || nt == 0) ? (stop ? 1 : 0) : 2;
+            for (int pass = 0; pass < npass && !done; ++pass) {
+                const int na = stop ? 1 : (pass == 0 ? nq : nt), nb = stop ? 1 : (pass == 0 ? nt : nq);
+                const int64_t a_src = pass == 0 ? q0 : tsrc, b_src = pass == 0 ? tsrc : q0;
+                const int64_t a_out = pass == 0 ? q0 : t0;
+                const int *bnorm = pass == 0 ? P.tnorm : P.qnorm;
+                const CUtensorMap *amap = pass == 0 ? &map_q : &map_t, *bmap = pass == 0 ? &map_t : &map_q;
+                for (int a0 = 0; a0 < na && !done; a0 += BM) {
+                    for (int b0 = 0; b0 < nb && !done; b0 += BN, ++u) {
+                        const int stage = u % STAGES;
+                        Slot *sl = &ring[u % RING];
+                        const int a_valid = min(BM, na - a0), b_valid = min(BN, nb - b0);
+                        if (lane == 0) mbar_wait(smem_u32(&bars->empty[stage]), ((u / STAGES) & 1) ^ 1);
+                        __syncwarp();
+                        if (stop) {
+                            if (lane == 0) { sl->flags = F_STOP; mbar_expect_tx(smem_u32(&bars->full[stage]), 0); }
+                            done = true;
+                            continue;
+                        }
+                        // exact-key constants of the B rows (all lanes), header (lane 0)
+#pragma unroll
+                        for (int c = lane; c < BN; c += 32)
+                            sl->ck[c] = c < b_valid ? (int)(((unsigned)__ldg(bnorm + b_src + b0 + c) << 8) | (unsigned)c) : I32_MAX;
+                        if (lane == 0) {
+                            sl->a_row0 = (int)(a_src + a0); sl->a_valid = a_valid;
+                            sl->b_row0 = (int)(b_src + b0); sl->b_valid = b_valid;
+                            sl->a_out0 = (int)(a_out + a0); sl->b_local0 = b0;
+                            sl->flags = (pass ? F_PASS1 : 0) | (b0 == 0 ? F_FIRST : 0) | (b0 + BN >= nb ? F_LAST : 0);
+                            sl->n_mma = (b_valid + 15) & ~15;
+                        }
+                        __syncwarp();
+                        if (lane == 0) {
+                            const int abox = (a_valid + BOX_ROWS - 1) / BOX_ROWS, bbox = (b_valid + BOX_ROWS - 1) / BOX_ROWS;
+                            const uint32_t fb = smem_u32(&bars->full[stage]);
+                            mbar_expect_tx(fb, (abox + bbox) * BOX_BYTES);
+                            const uint32_t sa = smem_u32(smem + SMEM_STAGES + stage * STAGE_BYTES);
+                            for (int i = 0; i < abox; ++i)
+                                tma_load_2d(sa + i * BOX_BYTES, amap, 0, (int)(a_src + a0) + i * BOX_ROWS, fb);
+                            for (int i = 0; i < bbox; ++i)
+                                tma_load_2d(sa + A_BYTES + i * BOX_BYTES, bmap, 0, (int)(b_src + b0) + i * BOX_ROWS, fb);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            for (int u = 0;; ++u) {
+                const int stage = u % STAGES, buf = u & 1;
+                mbar_wait(smem_u32(&bars->full[stage]), (u / STAGES) & 1);
+                tc_fence_after();
+                const Slot *sl = &ring[u % RING];
+                // the accumulator buffer must have been drained by the epilogue before its "full"
+                // barrier is signalled again -- for the stop unit too, or the barrier could run two
+                // phases ahead of a slow epilogue warp (parity aliasing)
+                mbar_wait(smem_u32(&bars->tmem_empty[buf]), ((u >> 1) & 1) ^ 1);
+                tc_fence_after();
+                if (sl->flags & F_STOP) {
+                    // tcgen05.commit arrives only after every MMA issued above has completed, so the
+                    // stop signal cannot overtake the accumulators still in flight
+                    umma_commit(smem_u32(&bars->tmem_full[buf]));
+                    break;
+                }
+                const uint32_t idesc = make_idesc(BM, sl->n_mma);
+                const uint32_t sa = smem_u32(smem + SMEM_STAGES + stage * STAGE_BYTES);
+                const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < FM_DIM / 32; ++k)
+                    umma_i8(tmem_base + buf * BN, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+                umma_commit(smem_u32(&bars->tmem_full[buf]));
+                umma_commit(smem_u32(&bars->empty[stage]));
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp - 4, lq = warp & 3, cq = ew >> 2;
+        const int row = lq * 32 + lane;
+        const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + cq * COLS_PER_WARP, 0);
+        int m1 = NONE_P, i1 = -1, m2 = NONE_P, i2 = -1;
+        for (int u = 0;; ++u) {
+            const int buf = u & 1;
+            mbar_wait(smem_u32(&bars->tmem_full[buf]), (u >> 1) & 1);
+            tc_fence_after();
+            const Slot *sl = &ring[u % RING];
+            const int flags = sl->flags;
+            if (flags & F_STOP) break;
+            const int b_valid = sl->b_valid, b_local0 = sl->b_local0;
+            const int ncols = min(max(b_valid - cq * COLS_PER_WARP, 0), COLS_PER_WARP);   // warp-uniform
+            int v0[32], v1[32];
+            if (ncols > 0) tmem_ld32(taddr0 + buf * BN, v0);
+            if (ncols > 32) tmem_ld32(taddr0 + buf * BN + 32, v1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
+            if (flags & F_FIRST) { m1 = m2 = NONE_P; i1 = i2 = -1; }
+            if (ncols > 0) {
+                const uint32_t cka = smem_u32(&sl->ck[cq * COLS_PER_WARP]);
+                int k1 = I32_MAX, k2 = I32_MAX;
+                const bool top1 = (flags & F_PASS1) != 0;     // warp-uniform
+#define FM_COLS(V, BASE)                                                                     \
+                {                                                                               \
+                    _Pragma("unroll") for (int c4 = 0; c4 < 8; ++c4) {                          \
+                        const int cb = BASE + c4 * 4;                                           \
+                        if (cb < ncols) {                                                       \
+                            const int4 ck = ld_shared_v4(cka + cb * 4);                         \
+                            int f0 = ck.x - 512 * V[c4 * 4 + 0], f1 = ck.y - 512 * V[c4 * 4 + 1]; \
+                            int f2 = ck.z - 512 * V[c4 * 4 + 2], f3 = ck.w - 512 * V[c4 * 4 + 3]; \
+                            if (cb + 4 > ncols) {   /* boundary group: columns past the last B row */ \
+                                f1 = cb + 1 < ncols ? f1 : I32_MAX;                             \
+                                f2 = cb + 2 < ncols ? f2 : I32_MAX;                             \
+                                f3 = cb + 3 < ncols ? f3 : I32_MAX;                             \
+                            }                                                                   \
+                            if (top1) { k1 = min(k1, min(min(f0, f1), min(f2, f3))); }          \
+                            else { insert2_key(f0, k1, k2); insert2_key(f1, k1, k2);            \
+                                   insert2_key(f2, k1, k2); insert2_key(f3, k1, k2); }          \
+                        }                                                                       \
+                    }                                                                           \
+                }
+                FM_COLS(v0, 0)
+                if (ncols > 32) FM_COLS(v1, 32)
+#undef FM_COLS
+                // merge the unit's minima into the row state (chunks arrive in increasing index)
+                const int p1 = k1 >> 8;
+                if (k1 != I32_MAX && p1 < m2) {
+                    const int j1 = b_local0 + (k1 & 255);
+                    if (p1 < m1) {
+                        const int p2 = k2 >> 8;
+                        if (k2 != I32_MAX && p2 < m1) { m2 = p2; i2 = b_local0 + (k2 & 255); }
+                        else { m2 = m1; i2 = i1; }
+                        m1 = p1; i1 = j1;
+                    } else {
+                        m2 = p1; i2 = j1;
+                    }
+                }
+            }
+            if (flags & F_LAST) {
+                // combine the four column quarters of each row, add |a_i|^2, write out
+                const bool pass1 = (flags & F_PASS1) != 0;
+                const int a_row0 = sl->a_row0, a_valid = sl->a_valid, a_out0 = sl->a_out0;
+                const int an = row < a_valid ? __ldg((pass1 ? P.tnorm : P.qnorm) + a_row0 + row) : 0;
+                skeys[(row * 4 + cq) * 2] = i1 < 0 ? FM_NONE_KEY : pack_key((uint32_t)(m1 + an), (uint32_t)i1);
+                skeys[(row * 4 + cq) * 2 + 1] = i2 < 0 ? FM_NONE_KEY : pack_key((uint32_t)(m2 + an), (uint32_t)i2);
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+                if (ew < 4) {
+                    const int r = ew * 32 + lane;
+                    unsigned long long a = skeys[r * 8], b = skeys[r * 8 + 1];
+#pragma unroll
+                    for (int c = 1; c < 4; ++c) merge2(a, b, skeys[r * 8 + 2 * c], skeys[r * 8 + 2 * c + 1]);
+                    if (r < a_valid) {
+                        const int64_t o = (int64_t)a_out0 + r;
+                        if (pass1) {
+                            P.t2q_idx[o] = a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a;
+                        } else {
+                            P.q2t_d2[o * 2] = (uint32_t)(a >> 32);
+                            P.q2t_d2[o * 2 + 1] = (uint32_t)(b >> 32);
+                            P.q2t_idx[o * 2] = a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a;
+                            P.q2t_idx[o * 2 + 1] = b == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)b;
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// crossCheck predicate per local query (needs both passes of the whole grid)
+__global__ void k_mutual(const int64_t *__restrict__ q_off, const int64_t *__restrict__ t_off,
+                         const int32_t *__restrict__ q2t_idx, const int32_t *__restrict__ t2q_idx,
+                         uint8_t *__restrict__ mutual) {
+    const int g = blockIdx.x;
+    const int64_t q0 = q_off[g], nq = q_off[g + 1] - q0, t0 = t_off[g];
+    for (int64_t i = threadIdx.x; i < nq; i += blockDim.x) {
+        const int32_t j = q2t_idx[(q0 + i) * 2];
+        mutual[q0 + i] = (j >= 0 && t2q_idx[t0 + j] == (int32_t)i) ? 1 : 0;
+    }
+}
+
+inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace gtc
+
+size_t grouped_tc_workspace_bytes(int64_t total_q, int64_t tpool_rows, bool gather) {
+    using namespace gtc;
+    return up256(256) + up256((size_t)(total_q + 8) * 4) + up256((size_t)(tpool_rows + 8) * 4) +
+           (gather ? up256((size_t)total_q * FM_DIM) : 0) + 256;
+}
+
+int launch_grouped_tc(const uint8_t *qpool, const int32_t *q_gather, const int64_t *q_off,
+                      const uint8_t *tpool, const int64_t *t_off, const int64_t *t_base, int32_t G,
+                      int64_t total_q, int64_t total_t, int64_t tpool_rows, uint32_t *q2t_d2,
+                      int32_t *q2t_idx, int32_t *t2q_idx, uint8_t *mutual, void *ws, size_t ws_bytes,
+                      cudaStream_t s) {
+    using namespace gtc;
+    if (ws_bytes < grouped_tc_workspace_bytes(total_q, tpool_rows, q_gather != nullptr)) {
+        set_error("grouped tcgen05 path: workspace too small");
+        return FM_ENOSPACE;
+    }
+    // every slot starts as "no neighbour"; units only exist for groups with both sides non-empty
+    if (total_q > 0) {
+        FM_CUDA_TRY(cudaMemsetAsync(q2t_d2, 0xFF, (size_t)total_q * 8, s));
+        FM_CUDA_TRY(cudaMemsetAsync(q2t_idx, 0xFF, (size_t)total_q * 8, s));
+    }
+    if (total_t > 0) FM_CUDA_TRY(cudaMemsetAsync(t2q_idx, 0xFF, (size_t)total_t * 4, s));
+    if (total_q > 0 && total_t > 0 && tpool_rows > 0) {
+        uint8_t *w = (uint8_t *)ws;
+        int *counter = (int *)w; w += up256(256);
+        int *qnorm = (int *)w; w += up256((size_t)(total_q + 8) * 4);
+        int *tnorm = (int *)w; w += up256((size_t)(tpool_rows + 8) * 4);
+        uint8_t *qpack = q_gather ? w : nullptr;
+        FM_CUDA_TRY(cudaMemsetAsync(counter, 0, 4, s));
+        k_pack_norms<<<(unsigned)((total_q * 8 + 255) / 256), 256, 0, s>>>(qpool, q_gather, total_q, qpack, qnorm);
+        k_pack_norms<<<(unsigned)((tpool_rows * 8 + 255) / 256), 256, 0, s>>>(tpool, nullptr, tpool_rows, nullptr, tnorm);
+        FM_CUDA_TRY(cudaGetLastError());
+        count_launch(2);
+        CUtensorMap map_q, map_t;
+        int rc;
+        if ((rc = make_map(&map_q, qpack ? qpack : qpool, total_q, FM_DIM, BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
+        if ((rc = make_map(&map_t, tpool, tpool_rows, FM_DIM, BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
+        static bool attr_set = false;
+        if (!attr_set) {
+            FM_CUDA_TRY(cudaFuncSetAttribute(k_grouped_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+            attr_set = true;
+        }
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        Params P{q_off, t_off, t_base, qnorm, tnorm, G, counter, q2t_d2, q2t_idx, t2q_idx};
+        const int grid = G < sms ? G : sms;
+        prof_begin(s);
+        k_grouped_tc<<<grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, P);
+        prof_end(s);
+        FM_CUDA_TRY(cudaGetLastError());
+        count_launch();
+    }
+    if (mutual && total_q > 0) {
+        k_mutual<<<G, 128, 0, s>>>(q_off, t_off, q2t_idx, t2q_idx, mutual);
+        FM_CUDA_TRY(cudaGetLastError());
+        count_launch();
+    }
+    return FM_OK;
+}
+
+}  // namespace fm

@@ -100,16 +100,17 @@ int fm_ratio_f32sqrt(const uint32_t *num_d2, int64_t num_stride, const uint32_t 
  *   (-1 if the group has no queries).  crossCheck keeps local query i iff
  *   t2q_idx[t_off[g] + q2t_idx[i][0]] == i - q_off[g].
  *   mutual [total_q] uint8 (may be NULL): that predicate, fused.
- * total_q / total_t = q_off[G] / t_off[G]; max_nq = an upper bound on the
- * number of queries of any group (host-known; avoids a device->host sync).
+ * total_q / total_t = q_off[G] / t_off[G]; tpool_rows = number of rows of tpool (only read
+ * when t_base != NULL, else total_t is used); max_nq = an upper bound on the number of queries
+ * of any group (host-known; avoids a device->host sync).  algo: FM_ALGO_AUTO picks the
+ * tcgen05 kernel on sm_100; FM_ALGO_MMA_SYNC forces the warp-MMA kernel.
  */
-size_t fm_grouped_workspace_bytes(int64_t total_q, int64_t total_t, int32_t G);
+size_t fm_grouped_workspace_bytes(int64_t total_q, int64_t total_t, int64_t tpool_rows, int32_t G);
 int fm_grouped_mutual_u8(const uint8_t *qpool, const int32_t *q_gather, const int64_t *q_off,
                          const uint8_t *tpool, const int64_t *t_off, const int64_t *t_base,
-                         int32_t G, int64_t total_q,
-                         int64_t total_t, int32_t max_nq, uint32_t *q2t_d2, int32_t *q2t_idx,
-                         int32_t *t2q_idx, uint8_t *mutual, void *ws, size_t ws_bytes,
-                         void *stream);
+                         int32_t G, int64_t total_q, int64_t total_t, int64_t tpool_rows,
+                         int32_t max_nq, uint32_t *q2t_d2, int32_t *q2t_idx, int32_t *t2q_idx,
+                         uint8_t *mutual, void *ws, size_t ws_bytes, int algo, void *stream);
 
 /*
  * Merge per-shard top-2 candidates (new: the exchange step of the target-

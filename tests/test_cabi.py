@@ -49,8 +49,8 @@ def test_version_and_argument_validation(lib):
     lib.fm_merge_top2.argtypes = [vp, ctypes.c_int32, i64, vp, vp, vp, vp]
     assert lib.fm_merge_top2(None, 2, 10, None, None, None, None) == -1
     lib.fm_grouped_workspace_bytes.restype = ctypes.c_size_t
-    lib.fm_grouped_workspace_bytes.argtypes = [i64, i64, ctypes.c_int32]
-    assert lib.fm_grouped_workspace_bytes(100, 50, 3) >= 50 * 8
+    lib.fm_grouped_workspace_bytes.argtypes = [i64, i64, i64, ctypes.c_int32]
+    assert lib.fm_grouped_workspace_bytes(100, 50, 50, 3) >= 50 * 8
     # M == 0 is a legal no-op
     assert lib.fm_top2_u8(None, 0, None, 0, 0, None, None, None, None, 0, 0, None) == 0
 

@@ -101,7 +101,12 @@ def test_ratio(cuda):
 
 
 def _check_grouped(qpool, q_off, tpool, t_off, cuda, q_gather=None):
-    args = dict(q_gather=None if q_gather is None else _dev(q_gather.astype(np.int32), cuda))
+    for algo in ALGOS:
+        _check_grouped_algo(qpool, q_off, tpool, t_off, cuda, q_gather, algo)
+
+
+def _check_grouped_algo(qpool, q_off, tpool, t_off, cuda, q_gather, algo):
+    args = dict(q_gather=None if q_gather is None else _dev(q_gather.astype(np.int32), cuda), algo=algo)
     d2, idx, t2q, mutual = backend.grouped_mutual(_dev(qpool, cuda), _dev(q_off, cuda), _dev(tpool, cuda),
                                                   _dev(t_off, cuda), **args)
     od2, oidx, ot2q = oracle.c_grouped_mutual(qpool, q_off, tpool, t_off, q_gather=q_gather)
@@ -144,6 +149,29 @@ def test_grouped_gather(cuda):
     noise = rng.integers(-6, 7, tpool.shape)
     tpool = np.clip(tpool.astype(np.int64) + noise, 0, 255).astype(np.uint8)
     _check_grouped(pool, q_off, tpool, t_off, cuda, q_gather=gather)
+
+
+def test_grouped_shared_cells_t_base(cuda):
+    """Many groups referencing the same resident cells through t_base (the flood-fill layout),
+    including groups larger than one unit (nq > 128, nt > 256) and more than 512 rows a side."""
+    rng = np.random.default_rng(12)
+    pool = synth.siftlike(3000, rng)
+    cells = synth.siftlike(2500, rng)
+    cell_start = np.array([0, 40, 41, 300, 900, 1700])
+    cell_cnt = np.array([40, 1, 259, 600, 800, 800])
+    which = rng.integers(0, 6, 60)
+    nq = rng.integers(1, 700, 60)
+    q_off = np.concatenate([[0], np.cumsum(nq)]).astype(np.int64)
+    t_off = np.concatenate([[0], np.cumsum(cell_cnt[which])]).astype(np.int64)
+    gather = rng.integers(0, 3000, int(q_off[-1])).astype(np.int32)
+    t_base = cell_start[which].astype(np.int64)
+    tcat = np.concatenate([cells[s:s + c] for s, c in zip(t_base, cell_cnt[which])])
+    od2, oidx, ot2q = oracle.c_grouped_mutual(pool, q_off, tcat, t_off, q_gather=gather)
+    for algo in ALGOS:
+        d2, idx, t2q, _ = backend.grouped_mutual(_dev(pool, cuda), _dev(q_off, cuda), _dev(cells, cuda), _dev(t_off, cuda),
+                                                 q_gather=_dev(gather, cuda), t_base=_dev(t_base, cuda), algo=algo)
+        assert np.array_equal(_u32(d2), od2) and np.array_equal(idx.cpu().numpy(), oidx)
+        assert np.array_equal(t2q.cpu().numpy(), ot2q)
 
 
 def test_grouped_config4_sample(cuda):
