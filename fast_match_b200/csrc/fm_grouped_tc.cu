@@ -58,7 +58,7 @@ struct __align__(8) Bars {
 constexpr int SMEM_STAGES = 0;
 constexpr int SMEM_RING = SMEM_STAGES + STAGES * STAGE_BYTES;
 constexpr int SMEM_KEYS = SMEM_RING + RING * (int)sizeof(Slot);       // [128 rows][4][2] u64
-constexpr int SMEM_BARS = SMEM_KEYS + BM * 4 * 2 * 8;
+constexpr int SMEM_BARS = SMEM_KEYS + 2 * BM * 4 * 2 * 8;          // double-buffered
 constexpr int SMEM_TOTAL = SMEM_BARS + (int)sizeof(Bars);
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
 
@@ -71,9 +71,36 @@ struct Params {
     int32_t *q2t_idx, *t2q_idx;
 };
 
-__device__ __forceinline__ void insert2_key(int k, int &k1, int &k2) {
-    k2 = max(k1, min(k2, k));   // second smallest of {k1, k2, k}
-    k1 = min(k1, k);
+#ifdef FM_TC_PROF
+__device__ unsigned long long g_gprof[16];
+#define GP_T(var) const long long var = clock64()
+#define GP_ACC(slot, a, b) _gp[slot] += (unsigned long long)((b) - (a))
+#else
+#define GP_T(var)
+#define GP_ACC(slot, a, b)
+#endif
+
+__device__ __forceinline__ int min3i(int a, int b, int c) { return __vimin3_s32(a, b, c); }
+__device__ __forceinline__ unsigned umin3i(unsigned a, unsigned b, unsigned c) { return __vimin3_u32(a, b, c); }
+
+// minimum of 32 keys (3-input tree, 16 ops)
+__device__ __forceinline__ int min32(const int (&v)[32]) {
+    int t[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) t[i] = min3i(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    t[10] = min(v[30], v[31]);
+    const int a = min3i(t[0], t[1], t[2]), b = min3i(t[3], t[4], t[5]), c = min3i(t[6], t[7], t[8]);
+    return min3i(min3i(a, b, c), t[9], t[10]);
+}
+// unsigned minimum of key - base over 32 keys (the key equal to base - 1 wraps to the maximum)
+__device__ __forceinline__ unsigned umin32(const int (&v)[32], int base) {
+    unsigned t[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i)
+        t[i] = umin3i((unsigned)(v[3 * i] - base), (unsigned)(v[3 * i + 1] - base), (unsigned)(v[3 * i + 2] - base));
+    t[10] = min((unsigned)(v[30] - base), (unsigned)(v[31] - base));
+    const unsigned a = umin3i(t[0], t[1], t[2]), b = umin3i(t[3], t[4], t[5]), c = umin3i(t[6], t[7], t[8]);
+    return umin3i(umin3i(a, b, c), t[9], t[10]);
 }
 
 // gather + norms: packed query rows (only when q_gather is given) and squared norms
@@ -105,6 +132,10 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     Slot *ring = (Slot *)(smem + SMEM_RING);
     unsigned long long *skeys = (unsigned long long *)(smem + SMEM_KEYS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef FM_TC_PROF
+    unsigned long long _gp[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const long long _gk0 = clock64();
+#endif
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
@@ -147,8 +178,11 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         const int stage = u % STAGES;
                         Slot *sl = &ring[u % RING];
                         const int a_valid = min(BM, na - a0), b_valid = min(BN, nb - b0);
+                        GP_T(_p0);
                         if (lane == 0) mbar_wait(smem_u32(&bars->empty[stage]), ((u / STAGES) & 1) ^ 1);
                         __syncwarp();
+                        GP_T(_p1);
+                        GP_ACC(0, _p0, _p1);
                         if (stop) {
                             if (lane == 0) { sl->flags = F_STOP; mbar_expect_tx(smem_u32(&bars->full[stage]), 0); }
                             done = true;
@@ -176,6 +210,11 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             for (int i = 0; i < bbox; ++i)
                                 tma_load_2d(sa + A_BYTES + i * BOX_BYTES, bmap, 0, (int)(b_src + b0) + i * BOX_ROWS, fb);
                         }
+                        GP_T(_p2);
+                        GP_ACC(1, _p1, _p2);
+#ifdef FM_TC_PROF
+                        _gp[2] += 1;
+#endif
                     }
                 }
             }
@@ -185,13 +224,18 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         if (lane == 0) {
             for (int u = 0;; ++u) {
                 const int stage = u % STAGES, buf = u & 1;
+                GP_T(_m0);
                 mbar_wait(smem_u32(&bars->full[stage]), (u / STAGES) & 1);
+                GP_T(_m1);
+                GP_ACC(3, _m0, _m1);
                 tc_fence_after();
                 const Slot *sl = &ring[u % RING];
                 // the accumulator buffer must have been drained by the epilogue before its "full"
                 // barrier is signalled again -- for the stop unit too, or the barrier could run two
                 // phases ahead of a slow epilogue warp (parity aliasing)
                 mbar_wait(smem_u32(&bars->tmem_empty[buf]), ((u >> 1) & 1) ^ 1);
+                GP_T(_m2);
+                GP_ACC(4, _m1, _m2);
                 tc_fence_after();
                 if (sl->flags & F_STOP) {
                     // tcgen05.commit arrives only after every MMA issued above has completed, so the
@@ -207,6 +251,8 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     umma_i8(tmem_base + buf * BN, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
                 umma_commit(smem_u32(&bars->tmem_full[buf]));
                 umma_commit(smem_u32(&bars->empty[stage]));
+                GP_T(_m3);
+                GP_ACC(5, _m2, _m3);
             }
         }
     } else if (warp >= 4) {
@@ -214,50 +260,81 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         const int ew = warp - 4, lq = warp & 3, cq = ew >> 2;
         const int row = lq * 32 + lane;
         const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + cq * COLS_PER_WARP, 0);
-        int m1 = NONE_P, i1 = -1, m2 = NONE_P, i2 = -1;
+        int m1 = NONE_P, i1 = -1, m2 = NONE_P, i2 = -1, nslab = 0;
         for (int u = 0;; ++u) {
             const int buf = u & 1;
+            GP_T(_e0);
             mbar_wait(smem_u32(&bars->tmem_full[buf]), (u >> 1) & 1);
+            GP_T(_e1);
+            GP_ACC(6, _e0, _e1);
             tc_fence_after();
             const Slot *sl = &ring[u % RING];
             const int flags = sl->flags;
             if (flags & F_STOP) break;
             const int b_valid = sl->b_valid, b_local0 = sl->b_local0;
             const int ncols = min(max(b_valid - cq * COLS_PER_WARP, 0), COLS_PER_WARP);   // warp-uniform
-            int v0[32], v1[32];
+            const bool top1 = (flags & F_PASS1) != 0;                                      // warp-uniform
+            // |a_i|^2 is only needed when the slab is written out: issue the load now, use it last
+            int an = 0;
+            if ((flags & F_LAST) && row < sl->a_valid) an = __ldg((top1 ? P.tnorm : P.qnorm) + sl->a_row0 + row);
+            int v0[32];
             if (ncols > 0) tmem_ld32(taddr0 + buf * BN, v0);
-            if (ncols > 32) tmem_ld32(taddr0 + buf * BN + 32, v1);
             tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
+            if (ncols <= 32) {      // nothing more to read: hand the accumulator back right away
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
+            }
+            GP_T(_e2);
+            GP_ACC(7, _e1, _e2);
             if (flags & F_FIRST) { m1 = m2 = NONE_P; i1 = i2 = -1; }
             if (ncols > 0) {
                 const uint32_t cka = smem_u32(&sl->ck[cq * COLS_PER_WARP]);
+                // Per 32 columns: exact keys in place of the accumulators (columns past the last B
+                // row -> INT_MAX), smallest key by a 3-input min tree and, for the top-2 pass, the
+                // runner-up = smallest key above it (keys are distinct or INT_MAX), obtained as the
+                // unsigned minimum of key - (kmin + 1).
                 int k1 = I32_MAX, k2 = I32_MAX;
-                const bool top1 = (flags & F_PASS1) != 0;     // warp-uniform
-#define FM_COLS(V, BASE)                                                                     \
+#define FM_HALF(V, BASE)                                                                     \
                 {                                                                               \
                     _Pragma("unroll") for (int c4 = 0; c4 < 8; ++c4) {                          \
                         const int cb = BASE + c4 * 4;                                           \
-                        if (cb < ncols) {                                                       \
+                        if (cb + 4 <= ncols) {                                                  \
                             const int4 ck = ld_shared_v4(cka + cb * 4);                         \
-                            int f0 = ck.x - 512 * V[c4 * 4 + 0], f1 = ck.y - 512 * V[c4 * 4 + 1]; \
-                            int f2 = ck.z - 512 * V[c4 * 4 + 2], f3 = ck.w - 512 * V[c4 * 4 + 3]; \
-                            if (cb + 4 > ncols) {   /* boundary group: columns past the last B row */ \
-                                f1 = cb + 1 < ncols ? f1 : I32_MAX;                             \
-                                f2 = cb + 2 < ncols ? f2 : I32_MAX;                             \
-                                f3 = cb + 3 < ncols ? f3 : I32_MAX;                             \
-                            }                                                                   \
-                            if (top1) { k1 = min(k1, min(min(f0, f1), min(f2, f3))); }          \
-                            else { insert2_key(f0, k1, k2); insert2_key(f1, k1, k2);            \
-                                   insert2_key(f2, k1, k2); insert2_key(f3, k1, k2); }          \
+                            V[c4 * 4 + 0] = ck.x - 512 * V[c4 * 4 + 0];                         \
+                            V[c4 * 4 + 1] = ck.y - 512 * V[c4 * 4 + 1];                         \
+                            V[c4 * 4 + 2] = ck.z - 512 * V[c4 * 4 + 2];                         \
+                            V[c4 * 4 + 3] = ck.w - 512 * V[c4 * 4 + 3];                         \
+                        } else if (cb < ncols) {                                                \
+                            const int4 ck = ld_shared_v4(cka + cb * 4);                         \
+                            V[c4 * 4 + 0] = ck.x - 512 * V[c4 * 4 + 0];                         \
+                            V[c4 * 4 + 1] = cb + 1 < ncols ? ck.y - 512 * V[c4 * 4 + 1] : I32_MAX; \
+                            V[c4 * 4 + 2] = cb + 2 < ncols ? ck.z - 512 * V[c4 * 4 + 2] : I32_MAX; \
+                            V[c4 * 4 + 3] = I32_MAX;                                            \
+                        } else {                                                                \
+                            V[c4 * 4 + 0] = V[c4 * 4 + 1] = V[c4 * 4 + 2] = V[c4 * 4 + 3] = I32_MAX; \
                         }                                                                       \
                     }                                                                           \
+                    const int h1 = min32(V);                                                    \
+                    int h2 = I32_MAX;                                                           \
+                    if (!top1) {                                                                \
+                        const int base = h1 + 1;                                                \
+                        const unsigned um = umin32(V, base);                                    \
+                        h2 = um >= (unsigned)(I32_MAX - base) ? I32_MAX : (int)(um + (unsigned)base); \
+                    }                                                                           \
+                    k2 = min3i(max(k1, h1), k2, h2);                                            \
+                    k1 = min(k1, h1);                                                           \
                 }
-                FM_COLS(v0, 0)
-                if (ncols > 32) FM_COLS(v1, 32)
-#undef FM_COLS
+                FM_HALF(v0, 0)
+                if (ncols > 32) {
+                    tmem_ld32(taddr0 + buf * BN + 32, v0);      // second half reuses the registers
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
+                    FM_HALF(v0, 32)
+                }
+#undef FM_HALF
                 // merge the unit's minima into the row state (chunks arrive in increasing index)
                 const int p1 = k1 >> 8;
                 if (k1 != I32_MAX && p1 < m2) {
@@ -272,38 +349,47 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     }
                 }
             }
+            GP_T(_e3);
+            GP_ACC(8, _e2, _e3);
             if (flags & F_LAST) {
-                // combine the four column quarters of each row, add |a_i|^2, write out
-                const bool pass1 = (flags & F_PASS1) != 0;
-                const int a_row0 = sl->a_row0, a_valid = sl->a_valid, a_out0 = sl->a_out0;
-                const int an = row < a_valid ? __ldg((pass1 ? P.tnorm : P.qnorm) + a_row0 + row) : 0;
-                skeys[(row * 4 + cq) * 2] = i1 < 0 ? FM_NONE_KEY : pack_key((uint32_t)(m1 + an), (uint32_t)i1);
-                skeys[(row * 4 + cq) * 2 + 1] = i2 < 0 ? FM_NONE_KEY : pack_key((uint32_t)(m2 + an), (uint32_t)i2);
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-                if (ew < 4) {
-                    const int r = ew * 32 + lane;
-                    unsigned long long a = skeys[r * 8], b = skeys[r * 8 + 1];
+                // combine the four column quarters of each row (the 4 warps of this lane quarter:
+                // own named barrier, double-buffered exchange area), add |a_i|^2, write out
+                const bool pass1 = top1;
+                const int a_valid = sl->a_valid, a_out0 = sl->a_out0;
+                unsigned long long *sk = skeys + (nslab & 1) * (BM * 8);
+                ++nslab;
+                sk[(row * 4 + cq) * 2] = i1 < 0 ? FM_NONE_KEY : pack_key((uint32_t)(m1 + an), (uint32_t)i1);
+                sk[(row * 4 + cq) * 2 + 1] = i2 < 0 ? FM_NONE_KEY : pack_key((uint32_t)(m2 + an), (uint32_t)i2);
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + lq) : "memory");
+                if (cq == 0 && row < a_valid) {
+                    unsigned long long a = sk[row * 8], b = sk[row * 8 + 1];
 #pragma unroll
-                    for (int c = 1; c < 4; ++c) merge2(a, b, skeys[r * 8 + 2 * c], skeys[r * 8 + 2 * c + 1]);
-                    if (r < a_valid) {
-                        const int64_t o = (int64_t)a_out0 + r;
-                        if (pass1) {
-                            P.t2q_idx[o] = a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a;
-                        } else {
-                            P.q2t_d2[o * 2] = (uint32_t)(a >> 32);
-                            P.q2t_d2[o * 2 + 1] = (uint32_t)(b >> 32);
-                            P.q2t_idx[o * 2] = a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a;
-                            P.q2t_idx[o * 2 + 1] = b == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)b;
-                        }
+                    for (int c = 1; c < 4; ++c) merge2(a, b, sk[row * 8 + 2 * c], sk[row * 8 + 2 * c + 1]);
+                    const int64_t o = (int64_t)a_out0 + row;
+                    if (pass1) {
+                        P.t2q_idx[o] = a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a;
+                    } else {
+                        *(uint2 *)(P.q2t_d2 + o * 2) = make_uint2((uint32_t)(a >> 32), (uint32_t)(b >> 32));
+                        *(int2 *)(P.q2t_idx + o * 2) = make_int2(a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a,
+                                                                 b == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)b);
                     }
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
             }
+            GP_T(_e4);
+            GP_ACC(9, _e3, _e4);
+#ifdef FM_TC_PROF
+            _gp[10] += 1;
+#endif
         }
     }
 
     tc_fence_before();
     __syncthreads();
+#ifdef FM_TC_PROF
+    if (lane == 0 && (warp == 0 || warp == 1 || warp == 4))
+        for (int i = 0; i < 11; ++i) if (_gp[i]) atomicAdd(&g_gprof[i], _gp[i]);
+    if (threadIdx.x == 0) { atomicAdd(&g_gprof[11], (unsigned long long)(clock64() - _gk0)); atomicAdd(&g_gprof[12], 1ull); }
+#endif
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
@@ -325,6 +411,15 @@ __global__ void k_mutual(const int64_t *__restrict__ q_off, const int64_t *__res
 inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace gtc
+
+#ifdef FM_TC_PROF
+extern "C" int fm_debug_gprof(unsigned long long *out16, int reset) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, gtc::g_gprof, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(gtc::g_gprof, z, sizeof(z)); }
+    return 0;
+}
+#endif
 
 size_t grouped_tc_workspace_bytes(int64_t total_q, int64_t tpool_rows, bool gather) {
     using namespace gtc;
