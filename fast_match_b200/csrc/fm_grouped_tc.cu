@@ -178,6 +178,14 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         const int stage = u % STAGES;
                         Slot *sl = &ring[u % RING];
                         const int a_valid = min(BM, na - a0), b_valid = min(BN, nb - b0);
+                        // |b_c|^2 of the unit's B rows: independent of the pipeline state, so the
+                        // loads are in flight while the warp waits for a free stage
+                        int bn[BN / 32];
+#pragma unroll
+                        for (int k = 0; k < BN / 32; ++k) {
+                            const int c = lane + 32 * k;
+                            bn[k] = (!stop && c < b_valid) ? __ldg(bnorm + b_src + b0 + c) : -1;
+                        }
                         GP_T(_p0);
                         if (lane == 0) mbar_wait(smem_u32(&bars->empty[stage]), ((u / STAGES) & 1) ^ 1);
                         __syncwarp();
@@ -188,10 +196,14 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             done = true;
                             continue;
                         }
-                        // exact-key constants of the B rows (all lanes), header (lane 0)
+                        const int abox = (a_valid + BOX_ROWS - 1) / BOX_ROWS, bbox = (b_valid + BOX_ROWS - 1) / BOX_ROWS;
+                        const uint32_t fb = smem_u32(&bars->full[stage]);
+                        // exact-key constants of the B rows (all lanes), header + barrier arming (lane 0)
 #pragma unroll
-                        for (int c = lane; c < BN; c += 32)
-                            sl->ck[c] = c < b_valid ? (int)(((unsigned)__ldg(bnorm + b_src + b0 + c) << 8) | (unsigned)c) : I32_MAX;
+                        for (int k = 0; k < BN / 32; ++k) {
+                            const int c = lane + 32 * k;
+                            sl->ck[c] = bn[k] >= 0 ? (int)(((unsigned)bn[k] << 8) | (unsigned)c) : I32_MAX;
+                        }
                         if (lane == 0) {
                             sl->a_row0 = (int)(a_src + a0); sl->a_valid = a_valid;
                             sl->b_row0 = (int)(b_src + b0); sl->b_valid = b_valid;
@@ -200,16 +212,14 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             sl->n_mma = (b_valid + 15) & ~15;
                         }
                         __syncwarp();
-                        if (lane == 0) {
-                            const int abox = (a_valid + BOX_ROWS - 1) / BOX_ROWS, bbox = (b_valid + BOX_ROWS - 1) / BOX_ROWS;
-                            const uint32_t fb = smem_u32(&bars->full[stage]);
-                            mbar_expect_tx(fb, (abox + bbox) * BOX_BYTES);
-                            const uint32_t sa = smem_u32(smem + SMEM_STAGES + stage * STAGE_BYTES);
-                            for (int i = 0; i < abox; ++i)
-                                tma_load_2d(sa + i * BOX_BYTES, amap, 0, (int)(a_src + a0) + i * BOX_ROWS, fb);
-                            for (int i = 0; i < bbox; ++i)
-                                tma_load_2d(sa + A_BYTES + i * BOX_BYTES, bmap, 0, (int)(b_src + b0) + i * BOX_ROWS, fb);
-                        }
+                        if (lane == 0) mbar_expect_tx(fb, (abox + bbox) * BOX_BYTES);
+                        __syncwarp();
+                        // one 32-row box per lane: lanes 0..3 the A slab, lanes 4..11 the B rows
+                        const uint32_t sa = smem_u32(smem + SMEM_STAGES + stage * STAGE_BYTES);
+                        if (lane < abox)
+                            tma_load_2d(sa + lane * BOX_BYTES, amap, 0, (int)(a_src + a0) + lane * BOX_ROWS, fb);
+                        else if (lane >= 4 && lane - 4 < bbox)
+                            tma_load_2d(sa + A_BYTES + (lane - 4) * BOX_BYTES, bmap, 0, (int)(b_src + b0) + (lane - 4) * BOX_ROWS, fb);
                         GP_T(_p2);
                         GP_ACC(1, _p1, _p2);
 #ifdef FM_TC_PROF
