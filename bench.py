@@ -329,10 +329,18 @@ def run_ours(args):
     bf16 = peaks.get("bf16_tflops")
     peak_tops = 2.0 * bf16 if bf16 else 2.0 * 1590.0
     ops = 2.0 * M_C3 * N_C3 * 128
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
     k_ms = kern_ms / max(kern_n, 1)
     achieved = ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
     roofline = {"bound": "tensor", "kernel": "k_top2_tc", "achieved": achieved, "peak": peak_tops, "unit": "TOP/s",
-                "frac": achieved / peak_tops, "traffic": None,
+                "frac": achieved / peak_tops,
+                "traffic": (traffic.get("k_top2_tc_c3_50k") or {}).get("bytes"),
+                "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json); "
+                                "the kernel is tensor-bound, its algorithmic HBM bytes are (M+N)*128 + 16*M = 13.6 MB",
                 "peak_source": ("2 x bf16_tflops of MEASURED_PEAKS.json (u8 tensor rate is twice bf16; the file has no "
                                 "int8 entry)" if bf16 else "2 x 1.59 PFLOP/s fallback"),
                 "frac_of_datasheet_4500": achieved / 4500.0, "kernel_ms": k_ms, "kernel_launches_timed": kern_n,
