@@ -82,15 +82,16 @@ constexpr int NONE_P = 0x7FFFFF;   // "no candidate": above every real partial d
 constexpr int EHALF_MAX = 255 * 255 * 15 + 254;   // digits 0..14 weigh 255, digit 15 weighs 1
 constexpr int EMAX = 2 * EHALF_MAX;
 constexpr int CG = 2 * EMAX;                      // the constant C of the filter
-__global__ void k_prepass(const uint8_t *__restrict__ q, int64_t M, const uint8_t *__restrict__ t,
-                          int64_t N, int64_t n_padded, int *__restrict__ qn,
-                          int *__restrict__ ckey, uint4 *__restrict__ digits) {
+__global__ void k_prepass(const uint8_t *__restrict__ q, int64_t M, int64_t m_padded,
+                          const uint8_t *__restrict__ t, int64_t N, int64_t n_padded,
+                          int *__restrict__ qn, int *__restrict__ gbound, int *__restrict__ ckey,
+                          uint4 *__restrict__ digits) {
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t row = gt >> 3;                  // 8 threads (16 B each) per descriptor
     const int sub = (int)(gt & 7);
-    const bool is_q = row < M;
-    const int64_t j = row - M;
-    const bool live = is_q || j < N;
+    const bool is_q = row < m_padded;
+    const int64_t j = row - m_padded;
+    const bool live = is_q ? row < M : j < N;
     unsigned s = 0;
     if (live) {
         const uint8_t *src = is_q ? q + row * FM_DIM : t + j * FM_DIM;
@@ -101,7 +102,13 @@ __global__ void k_prepass(const uint8_t *__restrict__ q, int64_t M, const uint8_
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (is_q) { if (sub == 0) qn[row] = (int)s; return; }
+    if (is_q) {
+        if (sub == 0) {
+            if (row < M) qn[row] = (int)s;
+            if (gbound) gbound[row] = NONE_P;     // cross-CTA bound on the second-best distance
+        }
+        return;
+    }
     if (j >= n_padded || sub > 1) return;
     if (j >= N) { if (sub == 0) ckey[j] = I32_MAX; return; }
     const int tn = (int)s;
@@ -192,7 +199,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
           const __grid_constant__ CUtensorMap map_x, int64_t M, int64_t N, int32_t t_index_base,
           int ntiles_total, int splits, const int *__restrict__ qn, const int *__restrict__ ckey,
-          uint32_t *__restrict__ out_d2,
+          int *__restrict__ gbound, uint32_t *__restrict__ out_d2,
           int32_t *__restrict__ out_idx, unsigned long long *__restrict__ out_keys,
           unsigned long long *__restrict__ partial) {
 #ifdef FM_TC_PROF
@@ -305,6 +312,8 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         // per-warp TMEM address of its 32 lanes x 64 columns (warp-uniform)
         const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + cq * COLS_PER_WARP, 0);
         const uint32_t full_a = smem_u32(&bars->tmem_full[0]), empty_a = smem_u32(&bars->tmem_empty[0]);
+        const int64_t grow0 = (int64_t)mblock * (SUBS * BM) + row_in_sub;
+        int gnext[SUBS] = {NONE_P, NONE_P}, gpub[SUBS] = {NONE_P, NONE_P};
 
         for (int it = 0; it < ntiles; ++it) {
             const int jtile = (tile_begin + it) * BN;
@@ -314,6 +323,25 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
             cp_async_wait1();
             __syncwarp();
             const uint32_t ck = ck_a + (it & 1) * (COLS_PER_WARP * 4);
+            if (gbound != nullptr && cq == 0) {
+                // Bounds also travel between the CTAs that sweep other target slices for the same
+                // rows (global memory, every 4th tile, same non-strict "+1" convention): read one
+                // tile ahead of use, publish with a fire-and-forget reduction.
+                const int ph = it & 3;
+                if (ph == 1) {
+#pragma unroll
+                    for (int s = 0; s < SUBS; ++s) red_shared_min_s32(sm2_a + s * BM * 4, gnext[s]);
+                } else if (ph == 0) {
+#pragma unroll
+                    for (int s = 0; s < SUBS; ++s) gnext[s] = ld_global_relaxed(gbound + grow0 + s * BM);
+                } else if (ph == 2) {
+#pragma unroll
+                    for (int s = 0; s < SUBS; ++s) {
+                        const int v = ld_shared_s32(sm2_a + s * BM * 4);
+                        if (v < gpub[s]) { red_global_min_s32(gbound + grow0 + s * BM, v); gpub[s] = v; }
+                    }
+                }
+            }
 #pragma unroll
             for (int s = 0; s < SUBS; ++s) {
                 const int shared_b = ld_shared_s32(sm2_a + s * BM * 4);
@@ -327,7 +355,9 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                 tc_fence_after();
                 int v0[32], v1[32];
                 tmem_ld32(taddr0 + s * BN, v0);
+#ifndef FM_EXPERIMENT_HALF_LD
                 tmem_ld32(taddr0 + s * BN + 32, v1);
+#endif
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -337,17 +367,28 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
 #endif
                 int bound = min(st[s].m2, shared_b);
                 int thr = (cg - bound) >> 1;        // acc' > thr  <=>  C - 2 acc' < bound
+#ifdef FM_EXPERIMENT_NO_SLOW   /* timing experiment only: results are wrong */
+#define FM_TRIG(x) ((x) > 0x7FFFFFF0)
+#else
+#define FM_TRIG(x) ((x) > thr)
+#endif
 #define FM_CHUNK(V, COL)                                                                  \
-                if (max16(V) > thr) {                                                        \
+                if (FM_TRIG(max16(V))) {                                                     \
                     const int m2_before = st[s].m2;                                          \
                     slow16(V, ck + (COL) * 4, jtile, bound, st[s]);                          \
                     if (st[s].m2 < m2_before) {                                              \
-                        atom_shared_min_s32(sm2_a + s * BM * 4, st[s].m2 + 1);               \
+                        red_shared_min_s32(sm2_a + s * BM * 4, st[s].m2 + 1);               \
                         bound = min(st[s].m2, bound);                                        \
                         thr = (cg - bound) >> 1;                                             \
                     }                                                                        \
                 }
+#if defined(FM_EXPERIMENT_NO_ALU)      /* timing experiment only: results are wrong */
+                if ((v0[0] ^ v0[31] ^ v1[0] ^ v1[31]) == 0x7FFFFFF1) st[s].m2 = 0;
+#elif defined(FM_EXPERIMENT_HALF_LD)   /* timing experiment only: results are wrong */
+                FM_CHUNK(v0, 0) FM_CHUNK(v0 + 16, 16)
+#else
                 FM_CHUNK(v0, 0) FM_CHUNK(v0 + 16, 16) FM_CHUNK(v1, 32) FM_CHUNK(v1 + 16, 48)
+#endif
 #undef FM_CHUNK
 #ifdef FM_TC_PROF
                 if (lane == 0) {
@@ -433,7 +474,7 @@ __global__ void k_merge_partial(const unsigned long long *__restrict__ partial, 
 struct Plan {
     int64_t mblocks, ntiles, npad;
     int splits;
-    size_t off_tn, off_ckey, off_digits, off_scal, off_qn, off_partial, total;
+    size_t off_tn, off_ckey, off_digits, off_scal, off_qn, off_gbound, off_partial, total;
 };
 
 static int sm_count() {
@@ -471,7 +512,8 @@ static Plan make_plan(int64_t M, int64_t N) {
     p.off_digits = up(p.off_ckey + (size_t)p.npad * 4);
     p.off_scal = up(p.off_digits + (size_t)p.npad * 32);        // [0] = min |t|^2, [1] = C
     p.off_qn = up(p.off_scal + 256);
-    p.off_partial = up(p.off_qn + (size_t)p.mblocks * SUBS * BM * 4);
+    p.off_gbound = up(p.off_qn + (size_t)p.mblocks * SUBS * BM * 4);
+    p.off_partial = up(p.off_gbound + (size_t)p.mblocks * SUBS * BM * 4);
     p.total = up(p.off_partial + (p.splits > 1 ? (size_t)p.splits * M * 16 : 0));
     return p;
 }
@@ -526,8 +568,10 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     if ((rc = make_map(&map_t, t, N, FM_DIM, BN, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
     if ((rc = make_map(&map_x, digits, N, 32, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) != FM_OK) return rc;
 
-    k_prepass<<<(unsigned)(((M + p.npad) * 8 + 255) / 256), 256, 0, s>>>(q, M, t, N, p.npad, qn, ckey,
-                                                                         (uint4 *)digits);
+    const int64_t mpad = p.mblocks * SUBS * BM;
+    int *gbound = p.splits > 1 ? (int *)(w + p.off_gbound) : nullptr;
+    k_prepass<<<(unsigned)(((mpad + p.npad) * 8 + 255) / 256), 256, 0, s>>>(q, M, mpad, t, N, p.npad, qn,
+                                                                            gbound, ckey, (uint4 *)digits);
     FM_CUDA_TRY(cudaGetLastError());
     count_launch();
 
@@ -539,7 +583,7 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     dim3 grid((unsigned)p.mblocks, (unsigned)p.splits);
     prof_begin(s);
     k_top2_tc<<<grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base,
-                                                 (int)p.ntiles, p.splits, qn, ckey, d2,
+                                                 (int)p.ntiles, p.splits, qn, ckey, gbound, d2,
                                                  idx, (unsigned long long *)keys, partial);
     prof_end(s);
     FM_CUDA_TRY(cudaGetLastError());

@@ -83,8 +83,16 @@ __device__ __forceinline__ int4 ld_shared_v4(uint32_t a) {
     asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
     return v;
 }
-__device__ __forceinline__ void atom_shared_min_s32(uint32_t a, int v) {
+__device__ __forceinline__ void red_shared_min_s32(uint32_t a, int v) {
     asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_global_min_s32(int *p, int v) {
+    asm volatile("red.relaxed.gpu.global.min.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_global_relaxed(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
