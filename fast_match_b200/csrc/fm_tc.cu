@@ -14,7 +14,8 @@
 //   * grid = (M-blocks, N-splits): the target range is cut into `splits` slices so that the
 //     grid fills the SMs evenly; per-slice candidates are merged by a small kernel.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..19 = epilogue (TMEM lane quarter = warp % 4, column quarter = (warp-4) / 4).
+// warps 4..19 = epilogue: two groups of 8 warps, one per sub-tile (TMEM lane quarter = warp % 4,
+// column half = bit 2 of the epilogue warp index).
 //
 // The epilogue is the bottleneck (K is only 128: 512 tensor cycles per 32768 outputs, and the
 // integer min/max pipe retires 64 lanes/clk/SM), so the per-output work is ~0.5 instruction:
@@ -25,8 +26,8 @@
 //     i.e. the largest accumulator of a row is its nearest neighbour (+25% MMA work buys a
 //     filter that needs no per-column term);
 //   * per 16 columns a 3-input max tree (0.5 op/output) is compared with the row's bound
-//     (C - m2)/2, m2 = current second-best partial distance (shared between the four warps
-//     that sweep the same row); only chunks that pass recompute exact integer keys
+//     (C - m2)/2, m2 = current second-best partial distance (shared between the two warps
+//     that sweep the same row and, via global memory, between CTAs on other target slices); only chunks that pass recompute exact integer keys
 //     (partial*256 + column) and update the row's top-2 with strict "<" in increasing column
 //     order, so ties keep the lowest index.  Results are exact for any u8 input.
 #include <cuda.h>
@@ -44,7 +45,7 @@ constexpr int BN = 256;                 // targets per tile (UMMA N)
 constexpr int STAGES = 4;
 constexpr int EPI_WARPS = 16;
 constexpr int NTHREADS = 128 + EPI_WARPS * 32;   // 640
-constexpr int COLS_PER_WARP = BN / (EPI_WARPS / 4);  // 64
+constexpr int COLS_PER_WARP = BN / 2;    // 128: a warp sweeps one column half of its sub-tile
 constexpr int A_BYTES = BM * FM_DIM;    // 16 KB per sub-tile
 constexpr int B_BYTES = BN * FM_DIM;    // 32 KB per stage
 constexpr int TMEM_COLS = 512;
@@ -60,12 +61,13 @@ constexpr int STAGE_BYTES = B_BYTES + BX_BYTES;
 constexpr int SMEM_A = 0;
 constexpr int SMEM_AX = SMEM_A + SUBS * A_BYTES;
 constexpr int SMEM_B = SMEM_AX + AX_BYTES;
-constexpr int SMEM_KEYS = SMEM_B + STAGES * STAGE_BYTES;        // [256 rows][4 col quarters][2] u64
-constexpr int SMEM_M2 = SMEM_KEYS + SUBS * BM * 4 * 2 * 8;      // [256 rows] shared second-best bound
-constexpr int SMEM_CK = SMEM_M2 + SUBS * BM * 4;                // [16 warps][2 slots][64] exact-key constants
+constexpr int SMEM_KEYS = SMEM_B + STAGES * STAGE_BYTES;        // [256 rows][2 column halves][2] u64
+constexpr int SMEM_M2 = SMEM_KEYS + SUBS * BM * 2 * 2 * 8;      // [256 rows] shared second-best bound
+constexpr int SMEM_CK = SMEM_M2 + SUBS * BM * 4;                // [16 warps][2 slots][128] exact-key constants
 constexpr int SMEM_BARS = SMEM_CK + EPI_WARPS * 2 * COLS_PER_WARP * 4;
 constexpr int SMEM_TOTAL = SMEM_BARS + (int)sizeof(Bars);
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;                   // slack for 1024-B alignment
+static_assert(SMEM_ALLOC <= 232448, "exceeds the 227 KB of shared memory a CTA can use");
 
 constexpr int I32_MAX = 0x7FFFFFFF;
 constexpr int NONE_P = 0x7FFFFF;   // "no candidate": above every real partial distance (<= 8323200)
@@ -220,7 +222,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
         mbar_init(smem_u32(&bars->a_full), 1);
-        for (int i = 0; i < SUBS; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_WARPS); }
+        for (int i = 0; i < SUBS; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_WARPS / SUBS); }
         fence_barrier_init();
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_t);
@@ -288,85 +290,81 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
+        // Two groups of 8 warps, one per sub-tile, so that the groups run half a period apart:
+        // while one group is waiting for its TMEM loads the other one keeps the integer pipe busy.
+        // Inside a group a warp owns 32 rows (its TMEM lane quarter) x 128 columns (a column
+        // half), swept in two passes of 64 columns; the accumulator goes back to the MMA warp as
+        // soon as the second pass has been read.
         const int ew = warp - 4;
+        const int s = ew >> 3;               // sub-tile of this warp's group
         const int lq = warp & 3;             // TMEM lane quarter this warp may touch
-        const int cq = ew >> 2;              // column quarter
+        const int ch = (ew >> 2) & 1;        // column half
         const int row_in_sub = lq * 32 + lane;
         constexpr int cg = CG;
-        RowState st[SUBS];
-        // sm2[row]: (second-best partial distance + 1) published by the four warps that sweep the
-        // same row -- "+1" because a sibling's candidate may carry a higher index (non-strict).
-        const uint32_t sm2_a = smem_u32(smem + SMEM_M2) + row_in_sub * 4;
-#pragma unroll
-        for (int s = 0; s < SUBS; ++s) {
-            st[s].m1 = st[s].m2 = NONE_P; st[s].i1 = st[s].i2 = -1;
-            if (cq == 0) st_shared_s32(sm2_a + s * BM * 4, NONE_P);
-        }
+        RowState st;
+        st.m1 = st.m2 = NONE_P; st.i1 = st.i2 = -1;
+        // sm2[row]: (second-best partial distance + 1) published by the two warps that sweep the
+        // same row (and by other CTAs, below) -- "+1" because a sibling's candidate may carry a
+        // higher index (non-strict bound).
+        const uint32_t sm2_a = smem_u32(smem + SMEM_M2) + (s * BM + row_in_sub) * 4;
+        if (ch == 0) st_shared_s32(sm2_a, NONE_P);
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
 
-        // exact-key constants of this warp's 64 columns: warp-private, double-buffered in smem
+        // exact-key constants of this warp's 128 columns: warp-private, double-buffered in smem
         const uint32_t ck_a = smem_u32(smem + SMEM_CK) + ew * (2 * COLS_PER_WARP * 4);
-        const int *ckg = ckey + (int64_t)tile_begin * BN + cq * COLS_PER_WARP + lane * 4;
-        if (lane < 16 && ntiles > 0) cp_async16(ck_a + lane * 16, ckg);
+        const int *ckg = ckey + (int64_t)tile_begin * BN + ch * COLS_PER_WARP + lane * 4;
+        if (ntiles > 0) cp_async16(ck_a + lane * 16, ckg);
         cp_async_commit();
-        // per-warp TMEM address of its 32 lanes x 64 columns (warp-uniform)
-        const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + cq * COLS_PER_WARP, 0);
-        const uint32_t full_a = smem_u32(&bars->tmem_full[0]), empty_a = smem_u32(&bars->tmem_empty[0]);
-        const int64_t grow0 = (int64_t)mblock * (SUBS * BM) + row_in_sub;
-        int gnext[SUBS] = {NONE_P, NONE_P}, gpub[SUBS] = {NONE_P, NONE_P};
+        // per-warp TMEM address of its 32 lanes x 128 columns (warp-uniform)
+        const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + s * BN + ch * COLS_PER_WARP, 0);
+        const uint32_t full_a = smem_u32(&bars->tmem_full[s]), empty_a = smem_u32(&bars->tmem_empty[s]);
+        const int64_t grow = (int64_t)mblock * (SUBS * BM) + s * BM + row_in_sub;
+        int gnext = NONE_P, gpub = NONE_P;
 
         for (int it = 0; it < ntiles; ++it) {
             const int jtile = (tile_begin + it) * BN;
-            if (lane < 16 && it + 1 < ntiles)
+            if (it + 1 < ntiles)
                 cp_async16(ck_a + ((it + 1) & 1) * (COLS_PER_WARP * 4) + lane * 16, ckg + (int64_t)(it + 1) * BN);
             cp_async_commit();
             cp_async_wait1();
             __syncwarp();
             const uint32_t ck = ck_a + (it & 1) * (COLS_PER_WARP * 4);
-            if (gbound != nullptr && cq == 0) {
+            if (gbound != nullptr && ch == 0) {
                 // Bounds also travel between the CTAs that sweep other target slices for the same
                 // rows (global memory, every 4th tile, same non-strict "+1" convention): read one
                 // tile ahead of use, publish with a fire-and-forget reduction.
                 const int ph = it & 3;
-                if (ph == 1) {
-#pragma unroll
-                    for (int s = 0; s < SUBS; ++s) red_shared_min_s32(sm2_a + s * BM * 4, gnext[s]);
-                } else if (ph == 0) {
-#pragma unroll
-                    for (int s = 0; s < SUBS; ++s) gnext[s] = ld_global_relaxed(gbound + grow0 + s * BM);
-                } else if (ph == 2) {
-#pragma unroll
-                    for (int s = 0; s < SUBS; ++s) {
-                        const int v = ld_shared_s32(sm2_a + s * BM * 4);
-                        if (v < gpub[s]) { red_global_min_s32(gbound + grow0 + s * BM, v); gpub[s] = v; }
-                    }
+                if (ph == 1) red_shared_min_s32(sm2_a, gnext);
+                else if (ph == 0) gnext = ld_global_relaxed(gbound + grow);
+                else if (ph == 2) {
+                    const int v = ld_shared_s32(sm2_a);
+                    if (v < gpub) { red_global_min_s32(gbound + grow, v); gpub = v; }
                 }
             }
+            const int shared_b = ld_shared_s32(sm2_a);
+#ifdef FM_TC_PROF
+            const long long _te0 = clock64();
+#endif
+            mbar_wait(full_a, it & 1);
+#ifdef FM_TC_PROF
+            const long long _te1 = clock64();
+#endif
+            tc_fence_after();
+            int bound = min(st.m2, shared_b);
+            int thr = (cg - bound) >> 1;        // acc' > thr  <=>  C - 2 acc' < bound
 #pragma unroll
-            for (int s = 0; s < SUBS; ++s) {
-                const int shared_b = ld_shared_s32(sm2_a + s * BM * 4);
-#ifdef FM_TC_PROF
-                const long long _te0 = clock64();
-#endif
-                mbar_wait(full_a + s * 8, it & 1);
-#ifdef FM_TC_PROF
-                const long long _te1 = clock64();
-#endif
-                tc_fence_after();
+            for (int pass = 0; pass < 2; ++pass) {
                 int v0[32], v1[32];
-                tmem_ld32(taddr0 + s * BN, v0);
+                tmem_ld32(taddr0 + pass * 64, v0);
 #ifndef FM_EXPERIMENT_HALF_LD
-                tmem_ld32(taddr0 + s * BN + 32, v1);
+                tmem_ld32(taddr0 + pass * 64 + 32, v1);
 #endif
                 tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty_a + s * 8);
-#ifdef FM_TC_PROF
-                const long long _te2 = clock64();
-#endif
-                int bound = min(st[s].m2, shared_b);
-                int thr = (cg - bound) >> 1;        // acc' > thr  <=>  C - 2 acc' < bound
+                if (pass == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty_a);
+                }
 #ifdef FM_EXPERIMENT_NO_SLOW   /* timing experiment only: results are wrong */
 #define FM_TRIG(x) ((x) > 0x7FFFFFF0)
 #else
@@ -374,53 +372,49 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
 #endif
 #define FM_CHUNK(V, COL)                                                                  \
                 if (FM_TRIG(max16(V))) {                                                     \
-                    const int m2_before = st[s].m2;                                          \
-                    slow16(V, ck + (COL) * 4, jtile, bound, st[s]);                          \
-                    if (st[s].m2 < m2_before) {                                              \
-                        red_shared_min_s32(sm2_a + s * BM * 4, st[s].m2 + 1);               \
-                        bound = min(st[s].m2, bound);                                        \
+                    const int m2_before = st.m2;                                             \
+                    slow16(V, ck + (pass * 64 + (COL)) * 4, jtile, bound, st);               \
+                    if (st.m2 < m2_before) {                                                 \
+                        red_shared_min_s32(sm2_a, st.m2 + 1);                                \
+                        bound = min(st.m2, bound);                                           \
                         thr = (cg - bound) >> 1;                                             \
                     }                                                                        \
                 }
 #if defined(FM_EXPERIMENT_NO_ALU)      /* timing experiment only: results are wrong */
-                if ((v0[0] ^ v0[31] ^ v1[0] ^ v1[31]) == 0x7FFFFFF1) st[s].m2 = 0;
+                if ((v0[0] ^ v0[31] ^ v1[0] ^ v1[31]) == 0x7FFFFFF1) st.m2 = 0;
 #elif defined(FM_EXPERIMENT_HALF_LD)   /* timing experiment only: results are wrong */
                 FM_CHUNK(v0, 0) FM_CHUNK(v0 + 16, 16)
 #else
                 FM_CHUNK(v0, 0) FM_CHUNK(v0 + 16, 16) FM_CHUNK(v1, 32) FM_CHUNK(v1 + 16, 48)
 #endif
 #undef FM_CHUNK
-#ifdef FM_TC_PROF
-                if (lane == 0) {
-                    const long long _te3 = clock64();
-                    _pacc[4] += (unsigned long long)(_te1 - _te0);   // wait tmem_full
-                    _pacc[5] += (unsigned long long)(_te2 - _te1);   // tmem load
-                    _pacc[6] += (unsigned long long)(_te3 - _te2);   // filter + updates
-                    _pacc[7] += 1ull;
-                }
-#endif
+#undef FM_TRIG
             }
+#ifdef FM_TC_PROF
+            if (lane == 0) {
+                const long long _te3 = clock64();
+                _pacc[4] += (unsigned long long)(_te1 - _te0);   // wait tmem_full
+                _pacc[6] += (unsigned long long)(_te3 - _te1);   // loads + filter + updates
+                _pacc[7] += 1ull;
+            }
+#endif
         }
-        // ---- merge the 4 column quarters of every row through shared memory
-#pragma unroll
-        for (int s = 0; s < SUBS; ++s) {
+        // ---- merge the 2 column halves of every row through shared memory
+        {
             const int r = s * BM + row_in_sub;
-            const int64_t grow = (int64_t)mblock * (SUBS * BM) + r;
             const int qnr = grow < M ? __ldg(qn + grow) : 0;
-            unsigned long long k1 = st[s].i1 < 0 ? FM_NONE_KEY
-                : pack_key((uint32_t)(st[s].m1 + qnr), (uint32_t)(st[s].i1 + t_index_base));
-            unsigned long long k2 = st[s].i2 < 0 ? FM_NONE_KEY
-                : pack_key((uint32_t)(st[s].m2 + qnr), (uint32_t)(st[s].i2 + t_index_base));
-            skeys[(r * 4 + cq) * 2] = k1;
-            skeys[(r * 4 + cq) * 2 + 1] = k2;
+            unsigned long long k1 = st.i1 < 0 ? FM_NONE_KEY
+                : pack_key((uint32_t)(st.m1 + qnr), (uint32_t)(st.i1 + t_index_base));
+            unsigned long long k2 = st.i2 < 0 ? FM_NONE_KEY
+                : pack_key((uint32_t)(st.m2 + qnr), (uint32_t)(st.i2 + t_index_base));
+            skeys[(r * 2 + ch) * 2] = k1;
+            skeys[(r * 2 + ch) * 2 + 1] = k2;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-        if (ew < 8) {
-            const int r = ew * 32 + lane;   // 256 rows, one thread each
-            const int64_t grow = (int64_t)mblock * (SUBS * BM) + r;
-            unsigned long long a = skeys[r * 8], b = skeys[r * 8 + 1];
-#pragma unroll
-            for (int c = 1; c < 4; ++c) merge2(a, b, skeys[r * 8 + 2 * c], skeys[r * 8 + 2 * c + 1]);
+        if (ch == 0) {
+            const int r = s * BM + row_in_sub;
+            unsigned long long a = skeys[r * 4], b = skeys[r * 4 + 1];
+            merge2(a, b, skeys[r * 4 + 2], skeys[r * 4 + 3]);
             if (grow < M) {
                 if (partial) {
                     partial[((int64_t)split * M + grow) * 2] = a;

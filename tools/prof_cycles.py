@@ -3,8 +3,7 @@ import ctypes, os, sys
 sys.path.insert(0, ".")
 from fast_match_b200 import build
 lib = os.path.join(os.path.dirname(build.LIB), "libfmatch_prof.so")
-if not os.path.exists(lib):
-    build.build(defines=["FM_TC_PROF"], out=lib)
+build.build(defines=["FM_TC_PROF"], out=lib)
 os.environ["FM_LIB"] = lib
 import torch
 from fast_match_b200 import backend, synth
@@ -21,4 +20,4 @@ for arg in sys.argv[1:] or ["50000"]:
     print(f"N={N} ctas={v[9]} tiles/cta={tiles/ctas:.1f} cycles/cta={v[8]/ctas:.0f} cycles/tile={v[8]/tiles:.0f}")
     print(f"  MMA thread per tile: wait full={v[0]/tiles:.0f} wait tmem_empty={v[1]/tiles:.0f}; producer wait empty={v[2]/tiles:.0f}")
     n = max(v[7], 1)
-    print(f"  epilogue per (tile,sub,warp): wait tmem_full={v[4]/n:.0f} load={v[5]/n:.0f} compute={v[6]/n:.0f}")
+    print(f"  epilogue per tile per warp (own sub): wait tmem_full={v[4]/n:.0f} loads+compute={v[6]/n:.0f}")
