@@ -382,6 +382,11 @@ def run_ours(args):
             line["sharded"] = sharded_leg(args, dev, world, rank, backend, sharded, barrier, max_over_ranks)
         except Exception as ex:  # noqa: BLE001
             line["sharded"] = {"error": repr(ex)}
+        if rank == 0 and world == 1:
+            try:
+                line["fastmatch_readme"] = fastmatch_leg(dev)
+            except Exception as ex:  # noqa: BLE001
+                line["fastmatch_readme"] = {"error": repr(ex)}
 
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
@@ -437,6 +442,46 @@ def grouped_leg(args, dev, peaks, backend):
                          "unit": "GB/s", "frac": (byts / (kms1 * 1e-3) / 1e9 / hbm) if kms1 else None,
                          "algorithmic_bytes": byts, "kernel_ms": kms1,
                          "tensor_ops": float((2 * 128 * nq.double() * nt.double()).sum())}}
+
+
+def fastmatch_leg(dev):
+    """configs[0]: the README example, Fast-Match graf img4 (query) -> img1 (target), through the
+    drop-in API fastmatch.match(query_cache, target_img, options)(tau).  SIFT (OpenCV, host) is part
+    of both arms; the matcher is the wave-batched grouped CUDA launch vs one cv2.BFMatcher call per
+    round (the reference's loop, restated in oracle/fastmatch_ref.py)."""
+    import cv2
+    import torch
+    from fast_match_b200 import cache as fm_cache, fastmatch
+    from oracle import fastmatch_ref
+    gold = os.path.join(ROOT, "tests", "golden")
+    img1 = cv2.imread(os.path.join(gold, "graf1.png"))
+    ref_cache = fastmatch_ref.RefMetricCache.from_image(os.path.join(gold, "graf4.png"))
+    o, th = ref_cache.original, ref_cache.thumb
+    mc = fm_cache.Metric_Cache.from_features(th["descriptors"], th["positions"], th["size"],
+                                             o["descriptors"], o["positions"], o["size"], {"device": str(dev)})
+    out = {"workload": "c1: README example, graf img4 -> img1, Metric_Cache, defaults (grid 50, margin 25, radius 100)"}
+    for tau in (0.7, 0.9):
+        res = {}
+        for name in ("ours", "reference_loop_cv2"):
+            best = None
+            for _ in range(2):
+                stats = {}
+                t0 = time.perf_counter()
+                if name == "ours":
+                    ms = fastmatch.match(mc, img1, {"stats": stats})(tau)
+                    torch.cuda.synchronize()
+                else:
+                    gm = fastmatch_ref.match(ref_cache, img1, {}, mutual=fastmatch_ref.cv2_mutual)
+                    ms = gm(tau)
+                    stats = {"rounds_evaluated": gm.rounds, "launches": gm.rounds}
+                dt = time.perf_counter() - t0
+                if best is None or dt < best[0]:
+                    best = (dt, len(ms), stats)
+            res[name] = {"s_per_pair": best[0], "pairs_per_s": 1.0 / best[0], "matches": best[1],
+                         "rounds": best[2].get("rounds_evaluated"), "matcher_calls": best[2].get("launches")}
+        res["identical_match_count"] = res["ours"]["matches"] == res["reference_loop_cv2"]["matches"]
+        out["tau_%.1f" % tau] = res
+    return out
 
 
 def sharded_leg(args, dev, world, rank, backend, sharded, barrier, max_over_ranks):
