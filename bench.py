@@ -480,8 +480,22 @@ def fastmatch_leg(dev):
             res[name] = {"s_per_pair": best[0], "pairs_per_s": 1.0 / best[0], "matches": best[1],
                          "rounds": best[2].get("rounds_evaluated"), "matcher_calls": best[2].get("launches")}
         res["identical_match_count"] = res["ours"]["matches"] == res["reference_loop_cv2"]["matches"]
+        try:   # precision under the shipped ground-truth homography (evaluate.py)
+            from fast_match_b200 import evaluate
+            H = evaluate.load_homography(os.path.join(gold, "graf_H1to4p.txt"))
+            res["fastmatch_inliers_5px"] = list(evaluate.inlier_fraction(fastmatch.match(mc, img1, {})(tau), H))
+            rp, _ = evaluate.ratio_match_positions(o["descriptors"], o["positions"], *_graf1_features(gold), tau)
+            res["ratiomatch_inliers_5px"] = list(evaluate.inlier_fraction(rp, H))
+        except Exception as ex:  # noqa: BLE001
+            res["inliers_error"] = repr(ex)
         out["tau_%.1f" % tau] = res
     return out
+
+
+def _graf1_features(gold):
+    import numpy as np
+    g = np.load(os.path.join(gold, "bf_golden.npz"))
+    return g["graf1_desc"], g["graf1_pos"]
 
 
 def sharded_leg(args, dev, world, rank, backend, sharded, barrier, max_over_ranks):

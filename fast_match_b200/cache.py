@@ -179,6 +179,17 @@ class Metric_Cache(object):
         self._fill(self.original, descriptors, [k.pt for k in keypoints], (img.shape[1], img.shape[0]))
         self.original["position_tree"] = BallTree(self.original["positions"], metric=metric)
 
+    @staticmethod
+    def _load_tree(data):
+        try:
+            raw = data["position_tree"]
+            raw = raw.tobytes() if raw.dtype == numpy.uint8 else raw.item()
+            tree = pickle.loads(raw)
+            tree.query_radius(numpy.zeros((1, 2)), r=1.0)
+            return tree
+        except Exception:  # noqa: BLE001
+            return BallTree(numpy.asarray(data["positions"], dtype=numpy.float64).reshape(-1, 2), metric="minkowski")
+
     # -- lookups ------------------------------------------------------------------
     def get_indices(self, x, y, radius, options={}):
         """Indices of the features within `radius` px of (x, y), nearest first (the order
@@ -223,12 +234,15 @@ class Metric_Cache(object):
         full, thumb = "%s/%s.npz" % (dir, key), "%s/%s_thumb.npz" % (dir, key)
         if not (os.path.isfile(full) and os.path.isfile(thumb)):
             return False
-        data, data_thumb = numpy.load(full, allow_pickle=False), numpy.load(thumb, allow_pickle=False)
+        # also reads the reference's layout (float32 integer-valued descriptors, FLANN distances,
+        # BallTree pickled by an older scikit-learn): descriptors are converted exactly, a tree
+        # that does not unpickle is rebuilt from the positions
+        data, data_thumb = numpy.load(full, allow_pickle=True), numpy.load(thumb, allow_pickle=True)
         self.thumb = {"positions": data_thumb["positions"],
                       "descriptors": matchutil.to_device(data_thumb["descriptors"], self.device),
                       "distances": data_thumb["distances"], "size": tuple(int(v) for v in data_thumb["size"])}
         self.original = {"descriptors": matchutil.to_device(data["descriptors"], self.device),
                          "positions": data["positions"], "distances": data["distances"],
-                         "position_tree": pickle.loads(data["position_tree"].tobytes()),
+                         "position_tree": self._load_tree(data),
                          "size": tuple(int(v) for v in data["size"])}
         return True

@@ -149,3 +149,23 @@ def test_two_gpu_sharded_nccl(cuda, tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29571", script], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_OK" in r.stdout
+
+
+def test_geometric_evaluation_with_shipped_homography(cuda):
+    """inlier fraction under graf's H1to4p for Ratio-Match (CUDA matcher) equals
+    the value computed from the frozen cv2 matches; Fast-Match's fraction is reported alongside."""
+    import cv2
+    from fast_match_b200 import evaluate
+    H = evaluate.load_homography(os.path.join(GOLD, "graf_H1to4p.txt"))
+    d, idx = G["graf41_knn2_dist"].astype(np.float64), G["graf41_knn2_idx"]
+    for tau, want_n in ((0.6, 24), (0.7, 66), (0.8, 281)):
+        pos, ratios = evaluate.ratio_match_positions(G["graf4_desc"], G["graf4_pos"], G["graf1_desc"], G["graf1_pos"], tau)
+        keep = np.nonzero(d[:, 0] / d[:, 1] < tau)[0]
+        ref = np.stack([G["graf4_pos"][keep], G["graf1_pos"][idx[keep, 0]]], 1).astype(np.float64)
+        assert len(pos) == want_n and (np.diff(ratios) >= 0).all()
+        assert evaluate.inlier_fraction(pos, H)[:2] == evaluate.inlier_fraction(ref, H)[:2]
+    img1 = cv2.imread(os.path.join(GOLD, "graf1.png"))
+    mc = fm_cache.Metric_Cache(os.path.join(GOLD, "graf4.png"), {"save": False})
+    ms = fastmatch.match(mc, img1, {})(0.7)
+    ok, n, frac = evaluate.inlier_fraction(ms, H)
+    assert n == len(ms) > 0 and 0.0 <= frac <= 1.0
