@@ -36,7 +36,7 @@ constexpr int BN = 256;
 constexpr int STAGES = 3;
 constexpr int EPI_WARPS = 16;
 constexpr int NTHREADS = 128 + EPI_WARPS * 32;
-constexpr int COLS_PER_WARP = BN / 4;
+constexpr int COLS_PER_WARP = BN / 2;    // a warp sweeps one column half of a unit
 constexpr int A_BYTES = BM * FM_DIM, B_BYTES = BN * FM_DIM, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int BOX_ROWS = 32, BOX_BYTES = BOX_ROWS * FM_DIM;
 constexpr int RING = 8;
@@ -53,12 +53,13 @@ struct __align__(16) Slot {
 struct __align__(8) Bars {
     unsigned long long full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
     uint32_t tmem_base, pad;
+    int stage_slot[STAGES + 1];     // ring slot of the unit that travels in each TMA stage
 };
 
 constexpr int SMEM_STAGES = 0;
 constexpr int SMEM_RING = SMEM_STAGES + STAGES * STAGE_BYTES;
-constexpr int SMEM_KEYS = SMEM_RING + RING * (int)sizeof(Slot);       // [128 rows][4][2] u64
-constexpr int SMEM_BARS = SMEM_KEYS + 2 * BM * 4 * 2 * 8;          // double-buffered
+constexpr int SMEM_KEYS = SMEM_RING + 2 * RING * (int)sizeof(Slot);   // [2 groups][2 bufs][128 rows][2 halves][2] u64
+constexpr int SMEM_BARS = SMEM_KEYS + 2 * 2 * BM * 2 * 2 * 8;
 constexpr int SMEM_TOTAL = SMEM_BARS + (int)sizeof(Bars);
 constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
 
@@ -129,7 +130,7 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     Bars *bars = (Bars *)(smem + SMEM_BARS);
-    Slot *ring = (Slot *)(smem + SMEM_RING);
+    Slot *ring = (Slot *)(smem + SMEM_RING);            // [2 accumulator buffers][RING]
     unsigned long long *skeys = (unsigned long long *)(smem + SMEM_KEYS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef FM_TC_PROF
@@ -139,7 +140,7 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_WARPS / 2); }
         fence_barrier_init();
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_t);
@@ -152,7 +153,9 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 
     if (warp == 0) {
         // ===================== producer: claims groups, emits units =====================
-        int u = 0;
+        // All B-chunks of a slab go to the same accumulator buffer (= the same epilogue group, which
+        // carries the rows' running minima across the chunks); consecutive slabs alternate buffers.
+        int u = 0, nslab = 0, nb[2] = {0, 0};
         bool done = false;
         while (!done) {
             int g = 0;
@@ -166,18 +169,21 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 t0 = P.t_off[g]; nt = (int)(P.t_off[g + 1] - t0);
                 tsrc = P.t_base ? P.t_base[g] : t0;
             }
-            const int npass = (stop || nq == 0 || nt == 0) ? (stop ? 1 : 0) : 2;
-            for (int pass = 0; pass < npass && !done; ++pass) {
-                const int na = stop ? 1 : (pass == 0 ? nq : nt), nb = stop ? 1 : (pass == 0 ? nt : nq);
+            // after the last group: one stop unit per accumulator buffer
+            const int npass = stop ? 2 : ((nq == 0 || nt == 0) ? 0 : 2);
+            for (int pass = 0; pass < npass; ++pass) {
+                const int na = stop ? 1 : (pass == 0 ? nq : nt), nbr = stop ? 1 : (pass == 0 ? nt : nq);
                 const int64_t a_src = pass == 0 ? q0 : tsrc, b_src = pass == 0 ? tsrc : q0;
                 const int64_t a_out = pass == 0 ? q0 : t0;
                 const int *bnorm = pass == 0 ? P.tnorm : P.qnorm;
                 const CUtensorMap *amap = pass == 0 ? &map_q : &map_t, *bmap = pass == 0 ? &map_t : &map_q;
-                for (int a0 = 0; a0 < na && !done; a0 += BM) {
-                    for (int b0 = 0; b0 < nb && !done; b0 += BN, ++u) {
+                for (int a0 = 0; a0 < na; a0 += BM, ++nslab) {
+                    const int buf = stop ? pass : (nslab & 1);
+                    for (int b0 = 0; b0 < nbr; b0 += BN, ++u) {
                         const int stage = u % STAGES;
-                        Slot *sl = &ring[u % RING];
-                        const int a_valid = min(BM, na - a0), b_valid = min(BN, nb - b0);
+                        const int slot_idx = buf * RING + (nb[buf]++ % RING);
+                        Slot *sl = &ring[slot_idx];
+                        const int a_valid = min(BM, na - a0), b_valid = min(BN, nbr - b0);
                         // |b_c|^2 of the unit's B rows: independent of the pipeline state, so the
                         // loads are in flight while the warp waits for a free stage
                         int bn[BN / 32];
@@ -191,13 +197,17 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         __syncwarp();
                         GP_T(_p1);
                         GP_ACC(0, _p0, _p1);
+                        const uint32_t fb = smem_u32(&bars->full[stage]);
                         if (stop) {
-                            if (lane == 0) { sl->flags = F_STOP; mbar_expect_tx(smem_u32(&bars->full[stage]), 0); }
-                            done = true;
+                            if (lane == 0) {
+                                sl->flags = F_STOP;
+                                bars->stage_slot[stage] = slot_idx;
+                                mbar_expect_tx(fb, 0);
+                            }
+                            __syncwarp();
                             continue;
                         }
                         const int abox = (a_valid + BOX_ROWS - 1) / BOX_ROWS, bbox = (b_valid + BOX_ROWS - 1) / BOX_ROWS;
-                        const uint32_t fb = smem_u32(&bars->full[stage]);
                         // exact-key constants of the B rows (all lanes), header + barrier arming (lane 0)
 #pragma unroll
                         for (int k = 0; k < BN / 32; ++k) {
@@ -208,8 +218,9 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             sl->a_row0 = (int)(a_src + a0); sl->a_valid = a_valid;
                             sl->b_row0 = (int)(b_src + b0); sl->b_valid = b_valid;
                             sl->a_out0 = (int)(a_out + a0); sl->b_local0 = b0;
-                            sl->flags = (pass ? F_PASS1 : 0) | (b0 == 0 ? F_FIRST : 0) | (b0 + BN >= nb ? F_LAST : 0);
+                            sl->flags = (pass ? F_PASS1 : 0) | (b0 == 0 ? F_FIRST : 0) | (b0 + BN >= nbr ? F_LAST : 0);
                             sl->n_mma = (b_valid + 15) & ~15;
+                            bars->stage_slot[stage] = slot_idx;
                         }
                         __syncwarp();
                         if (lane == 0) mbar_expect_tx(fb, (abox + bbox) * BOX_BYTES);
@@ -228,22 +239,27 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     }
                 }
             }
+            if (stop) done = true;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
-            for (int u = 0;; ++u) {
-                const int stage = u % STAGES, buf = u & 1;
+            int nb[2] = {0, 0}, stops = 0;
+            for (int u = 0; stops < 2; ++u) {
+                const int stage = u % STAGES;
                 GP_T(_m0);
                 mbar_wait(smem_u32(&bars->full[stage]), (u / STAGES) & 1);
                 GP_T(_m1);
                 GP_ACC(3, _m0, _m1);
                 tc_fence_after();
-                const Slot *sl = &ring[u % RING];
+                const int slot_idx = bars->stage_slot[stage];
+                const Slot *sl = &ring[slot_idx];
+                const int buf = slot_idx / RING;
+                const int kb = nb[buf]++;
                 // the accumulator buffer must have been drained by the epilogue before its "full"
                 // barrier is signalled again -- for the stop unit too, or the barrier could run two
                 // phases ahead of a slow epilogue warp (parity aliasing)
-                mbar_wait(smem_u32(&bars->tmem_empty[buf]), ((u >> 1) & 1) ^ 1);
+                mbar_wait(smem_u32(&bars->tmem_empty[buf]), (kb & 1) ^ 1);
                 GP_T(_m2);
                 GP_ACC(4, _m1, _m2);
                 tc_fence_after();
@@ -251,7 +267,9 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     // tcgen05.commit arrives only after every MMA issued above has completed, so the
                     // stop signal cannot overtake the accumulators still in flight
                     umma_commit(smem_u32(&bars->tmem_full[buf]));
-                    break;
+                    umma_commit(smem_u32(&bars->empty[stage]));
+                    ++stops;
+                    continue;
                 }
                 const uint32_t idesc = make_idesc(BM, sl->n_mma);
                 const uint32_t sa = smem_u32(smem + SMEM_STAGES + stage * STAGE_BYTES);
@@ -267,88 +285,86 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        const int ew = warp - 4, lq = warp & 3, cq = ew >> 2;
+        // Two groups of 8 warps, one per accumulator buffer; a warp owns 32 rows (its TMEM lane
+        // quarter) x 128 columns (a column half), swept in 32-column pieces.
+        const int ew = warp - 4, grp = ew >> 3, lq = warp & 3, ch = (ew >> 2) & 1;
         const int row = lq * 32 + lane;
-        const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + cq * COLS_PER_WARP, 0);
+        const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + grp * BN + ch * COLS_PER_WARP, 0);
+        const uint32_t full_a = smem_u32(&bars->tmem_full[grp]), empty_a = smem_u32(&bars->tmem_empty[grp]);
         int m1 = NONE_P, i1 = -1, m2 = NONE_P, i2 = -1, nslab = 0;
-        for (int u = 0;; ++u) {
-            const int buf = u & 1;
+        for (int k = 0;; ++k) {
             GP_T(_e0);
-            mbar_wait(smem_u32(&bars->tmem_full[buf]), (u >> 1) & 1);
+            mbar_wait(full_a, k & 1);
             GP_T(_e1);
             GP_ACC(6, _e0, _e1);
             tc_fence_after();
-            const Slot *sl = &ring[u % RING];
+            const Slot *sl = &ring[grp * RING + (k % RING)];
             const int flags = sl->flags;
             if (flags & F_STOP) break;
             const int b_valid = sl->b_valid, b_local0 = sl->b_local0;
-            const int ncols = min(max(b_valid - cq * COLS_PER_WARP, 0), COLS_PER_WARP);   // warp-uniform
+            const int ncols = min(max(b_valid - ch * COLS_PER_WARP, 0), COLS_PER_WARP);   // warp-uniform
             const bool top1 = (flags & F_PASS1) != 0;                                      // warp-uniform
             // |a_i|^2 is only needed when the slab is written out: issue the load now, use it last
             int an = 0;
             if ((flags & F_LAST) && row < sl->a_valid) an = __ldg((top1 ? P.tnorm : P.qnorm) + sl->a_row0 + row);
-            int v0[32];
-            if (ncols > 0) tmem_ld32(taddr0 + buf * BN, v0);
-            tmem_ld_wait();
-            if (ncols <= 32) {      // nothing more to read: hand the accumulator back right away
+            if (flags & F_FIRST) { m1 = m2 = NONE_P; i1 = i2 = -1; }
+            const uint32_t cka = smem_u32(&sl->ck[ch * COLS_PER_WARP]);
+            int k1 = I32_MAX, k2 = I32_MAX;
+            if (ncols == 0) {        // nothing to read: hand the accumulator back right away
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
+                if (lane == 0) mbar_arrive(empty_a);
+            }
+            // Per 32 columns: exact keys in place of the accumulators (columns past the last B row ->
+            // INT_MAX), smallest key by a 3-input min tree and, for the top-2 pass, the runner-up =
+            // smallest key above it (keys are distinct or INT_MAX), obtained as the unsigned minimum
+            // of key - (kmin + 1).  The accumulator goes back to the MMA warp after the last read.
+#pragma unroll 1
+            for (int base = 0; base < ncols; base += 32) {
+                int V[32];
+                tmem_ld32(taddr0 + base, V);
+                tmem_ld_wait();
+                if (base + 32 >= ncols) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty_a);
+                }
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const int cb = base + c4 * 4;
+                    if (cb + 4 <= ncols) {
+                        const int4 ck = ld_shared_v4(cka + cb * 4);
+                        V[c4 * 4 + 0] = ck.x - 512 * V[c4 * 4 + 0];
+                        V[c4 * 4 + 1] = ck.y - 512 * V[c4 * 4 + 1];
+                        V[c4 * 4 + 2] = ck.z - 512 * V[c4 * 4 + 2];
+                        V[c4 * 4 + 3] = ck.w - 512 * V[c4 * 4 + 3];
+                    } else if (cb < ncols) {
+                        const int4 ck = ld_shared_v4(cka + cb * 4);
+                        V[c4 * 4 + 0] = ck.x - 512 * V[c4 * 4 + 0];
+                        V[c4 * 4 + 1] = cb + 1 < ncols ? ck.y - 512 * V[c4 * 4 + 1] : I32_MAX;
+                        V[c4 * 4 + 2] = cb + 2 < ncols ? ck.z - 512 * V[c4 * 4 + 2] : I32_MAX;
+                        V[c4 * 4 + 3] = I32_MAX;
+                    } else {
+                        V[c4 * 4 + 0] = V[c4 * 4 + 1] = V[c4 * 4 + 2] = V[c4 * 4 + 3] = I32_MAX;
+                    }
+                }
+                const int h1 = min32(V);
+                int h2 = I32_MAX;
+                if (!top1) {
+                    const int hb = h1 + 1;
+                    const unsigned um = umin32(V, hb);
+                    h2 = um >= (unsigned)(I32_MAX - hb) ? I32_MAX : (int)(um + (unsigned)hb);
+                }
+                k2 = min3i(max(k1, h1), k2, h2);
+                k1 = min(k1, h1);
             }
             GP_T(_e2);
             GP_ACC(7, _e1, _e2);
-            if (flags & F_FIRST) { m1 = m2 = NONE_P; i1 = i2 = -1; }
+            // merge the unit's minima into the row state (chunks arrive in increasing index)
             if (ncols > 0) {
-                const uint32_t cka = smem_u32(&sl->ck[cq * COLS_PER_WARP]);
-                // Per 32 columns: exact keys in place of the accumulators (columns past the last B
-                // row -> INT_MAX), smallest key by a 3-input min tree and, for the top-2 pass, the
-                // runner-up = smallest key above it (keys are distinct or INT_MAX), obtained as the
-                // unsigned minimum of key - (kmin + 1).
-                int k1 = I32_MAX, k2 = I32_MAX;
-#define FM_HALF(V, BASE)                                                                     \
-                {                                                                               \
-                    _Pragma("unroll") for (int c4 = 0; c4 < 8; ++c4) {                          \
-                        const int cb = BASE + c4 * 4;                                           \
-                        if (cb + 4 <= ncols) {                                                  \
-                            const int4 ck = ld_shared_v4(cka + cb * 4);                         \
-                            V[c4 * 4 + 0] = ck.x - 512 * V[c4 * 4 + 0];                         \
-                            V[c4 * 4 + 1] = ck.y - 512 * V[c4 * 4 + 1];                         \
-                            V[c4 * 4 + 2] = ck.z - 512 * V[c4 * 4 + 2];                         \
-                            V[c4 * 4 + 3] = ck.w - 512 * V[c4 * 4 + 3];                         \
-                        } else if (cb < ncols) {                                                \
-                            const int4 ck = ld_shared_v4(cka + cb * 4);                         \
-                            V[c4 * 4 + 0] = ck.x - 512 * V[c4 * 4 + 0];                         \
-                            V[c4 * 4 + 1] = cb + 1 < ncols ? ck.y - 512 * V[c4 * 4 + 1] : I32_MAX; \
-                            V[c4 * 4 + 2] = cb + 2 < ncols ? ck.z - 512 * V[c4 * 4 + 2] : I32_MAX; \
-                            V[c4 * 4 + 3] = I32_MAX;                                            \
-                        } else {                                                                \
-                            V[c4 * 4 + 0] = V[c4 * 4 + 1] = V[c4 * 4 + 2] = V[c4 * 4 + 3] = I32_MAX; \
-                        }                                                                       \
-                    }                                                                           \
-                    const int h1 = min32(V);                                                    \
-                    int h2 = I32_MAX;                                                           \
-                    if (!top1) {                                                                \
-                        const int base = h1 + 1;                                                \
-                        const unsigned um = umin32(V, base);                                    \
-                        h2 = um >= (unsigned)(I32_MAX - base) ? I32_MAX : (int)(um + (unsigned)base); \
-                    }                                                                           \
-                    k2 = min3i(max(k1, h1), k2, h2);                                            \
-                    k1 = min(k1, h1);                                                           \
-                }
-                FM_HALF(v0, 0)
-                if (ncols > 32) {
-                    tmem_ld32(taddr0 + buf * BN + 32, v0);      // second half reuses the registers
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[buf]));
-                    FM_HALF(v0, 32)
-                }
-#undef FM_HALF
-                // merge the unit's minima into the row state (chunks arrive in increasing index)
                 const int p1 = k1 >> 8;
                 if (k1 != I32_MAX && p1 < m2) {
-                    const int j1 = b_local0 + (k1 & 255);
+                    const int j1 = b_local0 + ch * COLS_PER_WARP + (k1 & 255) - ch * COLS_PER_WARP;
                     if (p1 < m1) {
                         const int p2 = k2 >> 8;
                         if (k2 != I32_MAX && p2 < m1) { m2 = p2; i2 = b_local0 + (k2 & 255); }
@@ -362,21 +378,19 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             GP_T(_e3);
             GP_ACC(8, _e2, _e3);
             if (flags & F_LAST) {
-                // combine the four column quarters of each row (the 4 warps of this lane quarter:
-                // own named barrier, double-buffered exchange area), add |a_i|^2, write out
-                const bool pass1 = top1;
+                // combine the two column halves of each row (the 2 warps of this group and lane
+                // quarter: own named barrier, double-buffered exchange area), add |a_i|^2, write out
                 const int a_valid = sl->a_valid, a_out0 = sl->a_out0;
-                unsigned long long *sk = skeys + (nslab & 1) * (BM * 8);
+                unsigned long long *sk = skeys + ((grp * 2 + (nslab & 1)) * BM + row) * 4;
                 ++nslab;
-                sk[(row * 4 + cq) * 2] = i1 < 0 ? FM_NONE_KEY : pack_key((uint32_t)(m1 + an), (uint32_t)i1);
-                sk[(row * 4 + cq) * 2 + 1] = i2 < 0 ? FM_NONE_KEY : pack_key((uint32_t)(m2 + an), (uint32_t)i2);
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + lq) : "memory");
-                if (cq == 0 && row < a_valid) {
-                    unsigned long long a = sk[row * 8], b = sk[row * 8 + 1];
-#pragma unroll
-                    for (int c = 1; c < 4; ++c) merge2(a, b, sk[row * 8 + 2 * c], sk[row * 8 + 2 * c + 1]);
+                sk[ch * 2] = i1 < 0 ? FM_NONE_KEY : pack_key((uint32_t)(m1 + an), (uint32_t)i1);
+                sk[ch * 2 + 1] = i2 < 0 ? FM_NONE_KEY : pack_key((uint32_t)(m2 + an), (uint32_t)i2);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + grp * 4 + lq) : "memory");
+                if (ch == 0 && row < a_valid) {
+                    unsigned long long a = sk[0], b = sk[1];
+                    merge2(a, b, sk[2], sk[3]);
                     const int64_t o = (int64_t)a_out0 + row;
-                    if (pass1) {
+                    if (top1) {
                         P.t2q_idx[o] = a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a;
                     } else {
                         *(uint2 *)(P.q2t_d2 + o * 2) = make_uint2((uint32_t)(a >> 32), (uint32_t)(b >> 32));
