@@ -396,6 +396,13 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _traffic(key):
+    try:
+        return (json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key) or {}).get("bytes")
+    except Exception:
+        return None
+
+
 def grouped_leg(args, dev, peaks, backend):
     import torch
     G = args.groups
@@ -438,8 +445,9 @@ def grouped_leg(args, dev, peaks, backend):
     return {"workload": "c4: %d groups, n_q,n_t ~ U[32,512], packed, one grouped launch" % G, "ms": ms,
             "groups_per_s": G / (ms * 1e-3), "query_descriptors_per_s": Q / (ms * 1e-3),
             "total_q": Q, "total_t": T, "mutual_matches": None,
-            "roofline": {"bound": "hbm", "achieved": byts / (kms1 * 1e-3) / 1e9 if kms1 else None, "peak": hbm,
+            "roofline": {"bound": "hbm", "kernel": "k_grouped_tc", "achieved": byts / (kms1 * 1e-3) / 1e9 if kms1 else None, "peak": hbm,
                          "unit": "GB/s", "frac": (byts / (kms1 * 1e-3) / 1e9 / hbm) if kms1 else None,
+                         "traffic": _traffic("k_grouped_tc_c4"),
                          "algorithmic_bytes": byts, "kernel_ms": kms1,
                          "tensor_ops": float((2 * 128 * nq.double() * nt.double()).sum())}}
 

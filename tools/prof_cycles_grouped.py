@@ -15,4 +15,4 @@ ctas = v[12]; units = v[2]; eu = v[10]
 print("ms", a["ms"], "ctas", ctas, "units(all calls)", units, "cycles/cta/call", v[11] / ctas)
 print("producer per unit: wait empty %.0f  own work %.0f" % (v[0] / units, v[1] / units))
 print("mma per unit: wait full %.0f  wait tmem_empty %.0f  issue %.0f" % (v[3] / units, v[4] / units, v[5] / units))
-print("epilogue(warp4) per unit: wait tmem_full %.0f  load %.0f  compute %.0f  last/merge %.0f" % (v[6] / eu, v[7] / eu, v[8] / eu, v[9] / eu))
+print("epilogue(warp4 = group 0) per own unit: wait tmem_full %.0f  loads+keys+minima %.0f  state merge %.0f  write-out %.0f" % (v[6] / eu, v[7] / eu, v[8] / eu, v[9] / eu))
