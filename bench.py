@@ -263,13 +263,12 @@ def run_ours(args):
     # ---------------- headline: c3, one pair per rank, inputs resident in HBM ----------------
     q_np, t_np = synth.make_pair(M_C3, N_C3, seed=1237 + rank)
     q_dev, t_dev = torch.from_numpy(q_np).to(dev), torch.from_numpy(t_np).to(dev)
-    out = (torch.empty((M_C3, 2), dtype=torch.int32, device=dev), torch.empty((M_C3, 2), dtype=torch.int32, device=dev), None)
+    out = (torch.empty((M_C3, 2), dtype=torch.int32, device=dev), torch.empty((M_C3, 2), dtype=torch.int32, device=dev),
+           torch.empty(M_C3, dtype=torch.uint8, device=dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    def step():
-        d2, idx = backend.top2(q_dev, t_dev, out=out)[:2]
-        _, mask = backend.ratio(d2[:, 0], den_d2=d2[:, 1], tau=TAU, want_ratio=False)
-        return mask
+    def step():   # exact top-2 + Lowe ratio test, fused (fm_ratio_match_u8)
+        return backend.ratio_match(q_dev, t_dev, TAU, out=out)[3]
 
     for _ in range(args.warmup):
         step()

@@ -37,6 +37,7 @@ def lib():
         L.fm_top2_workspace_bytes.argtypes = [i64, i64]
         L.fm_top2_workspace_bytes.restype = sz
         L.fm_top2_u8.argtypes = [vp, i64, vp, i64, i32, vp, vp, vp, vp, sz, ctypes.c_int, vp]
+        L.fm_ratio_match_u8.argtypes = [vp, i64, vp, i64, ctypes.c_double, vp, vp, vp, vp, vp, sz, ctypes.c_int, vp]
         L.fm_ratio_f32sqrt.argtypes = [vp, i64, vp, i64, vp, i64, ctypes.c_double, vp, vp, vp]
         L.fm_grouped_workspace_bytes.argtypes = [i64, i64, i64, i32]
         L.fm_grouped_workspace_bytes.restype = sz
@@ -115,6 +116,28 @@ def top2(q, t, t_index_base=0, algo=FM_ALGO_AUTO, want_keys=False, out=None):
                             _ptr(keys), _ptr(ws), ws.numel(), int(algo), _stream(dev)),
                "fm_top2_u8")
     return (d2, idx, keys) if want_keys else (d2, idx)
+
+
+def ratio_match(q, t, tau, algo=FM_ALGO_AUTO, want_ratio=False, out=None):
+    """Ratio-Match in one call: exact top-2 with the ratio test fused into the kernel write-out.
+    Returns (d2, idx, ratio float64 | None, mask bool)."""
+    q, t = _desc(q, "q"), _desc(t, "t")
+    M, N = q.shape[0], t.shape[0]
+    dev = q.device
+    if out is None:
+        d2 = torch.empty((M, 2), dtype=torch.int32, device=dev)
+        idx = torch.empty((M, 2), dtype=torch.int32, device=dev)
+        mask = torch.empty(M, dtype=torch.uint8, device=dev)
+    else:
+        d2, idx, mask = out
+    r = torch.empty(M, dtype=torch.float64, device=dev) if want_ratio else None
+    L = lib()
+    ws = _workspace(dev, L.fm_top2_workspace_bytes(M, N))
+    with torch.cuda.device(dev):
+        _check(L.fm_ratio_match_u8(_ptr(q), M, _ptr(t), N, float(tau), _ptr(d2), _ptr(idx), _ptr(r),
+                                   _ptr(mask), _ptr(ws), ws.numel(), int(algo), _stream(dev)),
+               "fm_ratio_match_u8")
+    return d2, idx, r, mask.bool()
 
 
 def ratio(num_d2, den_d2=None, den_f32=None, tau=0.7, want_ratio=True):

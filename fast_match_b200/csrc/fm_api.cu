@@ -62,13 +62,9 @@ __global__ void k_ratio(const uint32_t *__restrict__ num_d2, int64_t num_stride,
         uint32_t n = num_d2[i * num_stride];
         uint32_t dd = den_f32 ? 0u : den_d2[i * den_stride];
         double r;
-        if (n == FM_NONE_D2 || dd == FM_NONE_D2) {
-            r = __longlong_as_double(0x7FF0000000000000ll);
-        } else {
-            double num = (double)__fsqrt_rn((float)n);
-            double den = den_f32 ? (double)den_f32[i] : (double)__fsqrt_rn((float)dd);
-            r = __ddiv_rn(num, den);
-        }
+        if (!den_f32) r = ratio_f32sqrt(n, dd);
+        else if (n == FM_NONE_D2) r = __longlong_as_double(0x7FF0000000000000ll);
+        else r = __ddiv_rn((double)__fsqrt_rn((float)n), (double)den_f32[i]);
         if (ratio) ratio[i] = r;
         if (mask) mask[i] = r < tau ? 1 : 0;
     }
@@ -163,20 +159,20 @@ int fm_device_caps(int device, int *sm_major, int *sm_minor, int *sm_count, int 
 
 size_t fm_top2_workspace_bytes(int64_t M, int64_t N) { return fm::top2_tc_workspace_bytes(M, N); }
 
-int fm_top2_u8(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int32_t t_index_base,
-               uint32_t *d2, int32_t *idx, uint64_t *keys, void *ws, size_t ws_bytes, int algo,
-               void *stream) {
+static int top2_impl(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int32_t t_index_base,
+                     uint32_t *d2, int32_t *idx, uint64_t *keys, fm::RatioOut rout, void *ws,
+                     size_t ws_bytes, int algo, void *stream, const char *who) {
     if (M < 0 || N < 0 || (M > 0 && (!q || !d2 || !idx)) || (N > 0 && !t)) {
-        set_error("fm_top2_u8: bad argument (M=%lld N=%lld q=%p t=%p d2=%p idx=%p)", (long long)M,
+        set_error("%s: bad argument (M=%lld N=%lld q=%p t=%p d2=%p idx=%p)", who, (long long)M,
                   (long long)N, (const void *)q, (const void *)t, (void *)d2, (void *)idx);
         return FM_EINVAL;
     }
     if (!aligned16(q) || !aligned16(t)) {
-        set_error("fm_top2_u8: descriptor pointers must be 16-byte aligned");
+        set_error("%s: descriptor pointers must be 16-byte aligned", who);
         return FM_EINVAL;
     }
     if (N + (int64_t)t_index_base > 0x7FFFFFFFll || M > 0x7FFFFFFFll) {
-        set_error("fm_top2_u8: index range exceeds int32");
+        set_error("%s: index range exceeds int32", who);
         return FM_EINVAL;
     }
     if (M == 0) return FM_OK;
@@ -184,7 +180,7 @@ int fm_top2_u8(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int32_t
     bool use_tc;
     if (algo == FM_ALGO_TCGEN05) {
         if (!fm::tc_supported()) {
-            set_error("fm_top2_u8: FM_ALGO_TCGEN05 requested but the device is not sm_100");
+            set_error("%s: FM_ALGO_TCGEN05 requested but the device is not sm_100", who);
             return FM_EUNSUPPORTED;
         }
         use_tc = true;
@@ -194,18 +190,37 @@ int fm_top2_u8(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int32_t
         // the tensor-core kernel pays a fixed set-up cost; tiny problems stay on the warp-MMA path
         use_tc = fm::tc_supported() && N >= 256 && M * N >= (int64_t)1 << 20;
     } else {
-        set_error("fm_top2_u8: unknown algo %d", algo);
+        set_error("%s: unknown algo %d", who, algo);
         return FM_EINVAL;
     }
     if (use_tc) {
         if (ws_bytes < fm::top2_tc_workspace_bytes(M, N) || (!ws && fm::top2_tc_workspace_bytes(M, N))) {
-            set_error("fm_top2_u8: workspace too small (%zu < %zu)", ws_bytes,
-                      fm::top2_tc_workspace_bytes(M, N));
+            set_error("%s: workspace too small (%zu < %zu)", who, ws_bytes, fm::top2_tc_workspace_bytes(M, N));
             return FM_ENOSPACE;
         }
-        return fm::launch_top2_tc(q, M, t, N, t_index_base, d2, idx, keys, ws, ws_bytes, s);
+        return fm::launch_top2_tc(q, M, t, N, t_index_base, d2, idx, keys, rout, ws, ws_bytes, s);
     }
-    return fm::launch_sweep_mma_dense(q, M, t, N, t_index_base, d2, idx, keys, s);
+    int rc = fm::launch_sweep_mma_dense(q, M, t, N, t_index_base, d2, idx, keys, s);
+    if (rc != FM_OK || (!rout.ratio && !rout.mask)) return rc;
+    return fm_ratio_f32sqrt(d2, 2, d2 + 1, 2, nullptr, M, rout.tau, rout.ratio, rout.mask, stream);
+}
+
+int fm_top2_u8(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int32_t t_index_base,
+               uint32_t *d2, int32_t *idx, uint64_t *keys, void *ws, size_t ws_bytes, int algo,
+               void *stream) {
+    return top2_impl(q, M, t, N, t_index_base, d2, idx, keys, fm::RatioOut{0.0, nullptr, nullptr}, ws,
+                     ws_bytes, algo, stream, "fm_top2_u8");
+}
+
+int fm_ratio_match_u8(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, double tau,
+                      uint32_t *d2, int32_t *idx, double *ratio, uint8_t *mask, void *ws,
+                      size_t ws_bytes, int algo, void *stream) {
+    if (M > 0 && !ratio && !mask) {
+        set_error("fm_ratio_match_u8: give ratio and/or mask");
+        return FM_EINVAL;
+    }
+    return top2_impl(q, M, t, N, 0, d2, idx, nullptr, fm::RatioOut{tau, ratio, mask}, ws, ws_bytes, algo,
+                     stream, "fm_ratio_match_u8");
 }
 
 int fm_ratio_f32sqrt(const uint32_t *num_d2, int64_t num_stride, const uint32_t *den_d2,
@@ -366,17 +381,17 @@ int fm_top2_host_u8(const uint8_t *q_host, int64_t M, const uint8_t *t_host, int
     FM_CUDA_TRY(cudaMemcpyAsync(c.dev + o_q, qsrc, qb, cudaMemcpyHostToDevice, c.stream));
     if (tb) FM_CUDA_TRY(cudaMemcpyAsync(c.dev + o_t, tsrc, tb, cudaMemcpyHostToDevice, c.stream));
     uint32_t *d2_dev = (uint32_t *)(c.dev + o_d2);
-    rc = fm_top2_u8(c.dev + o_q, M, c.dev + o_t, N, 0, d2_dev, (int32_t *)(c.dev + o_idx), nullptr,
-                    c.dev + o_ws, up256(wsb), FM_ALGO_AUTO, c.stream);
+    if (mask_host)     // Lowe ratio test d1/d2 < tau fused into the same launch sequence
+        rc = fm_ratio_match_u8(c.dev + o_q, M, c.dev + o_t, N, tau, d2_dev, (int32_t *)(c.dev + o_idx),
+                               nullptr, c.dev + o_mask, c.dev + o_ws, up256(wsb), FM_ALGO_AUTO, c.stream);
+    else
+        rc = fm_top2_u8(c.dev + o_q, M, c.dev + o_t, N, 0, d2_dev, (int32_t *)(c.dev + o_idx), nullptr,
+                        c.dev + o_ws, up256(wsb), FM_ALGO_AUTO, c.stream);
     if (rc != FM_OK) return rc;
     if (dist_host) {
         k_dist<<<grid_for(M * 2, 256), 256, 0, c.stream>>>(d2_dev, (float *)(c.dev + o_dist), M * 2);
         FM_CUDA_TRY(cudaGetLastError());
         fm::count_launch();
-    }
-    if (mask_host) {   // Lowe ratio test d1/d2 < tau, fused into the same call
-        rc = fm_ratio_f32sqrt(d2_dev, 2, d2_dev + 1, 2, nullptr, M, tau, nullptr, c.dev + o_mask, c.stream);
-        if (rc != FM_OK) return rc;
     }
     const bool out_pinned = is_device_accessible_host(d2_host) && is_device_accessible_host(idx_host) &&
                             (!dist_host || is_device_accessible_host(dist_host)) &&

@@ -45,6 +45,26 @@ __device__ __forceinline__ void merge2(unsigned long long &a1, unsigned long lon
     a2 = hi < h2 ? hi : h2;
 }
 
+// Lowe ratio test on squared distances, exactly as the reference computes it from DMatch
+// distances (fastmatch.pyx:124,165; Classic Matching.ipynb cell 3): float32 sqrt, float64 divide.
+__device__ __forceinline__ double ratio_f32sqrt(uint32_t num_d2, uint32_t den_d2) {
+    if (num_d2 == FM_NONE_D2 || den_d2 == FM_NONE_D2) return __longlong_as_double(0x7FF0000000000000ll);
+    return __ddiv_rn((double)__fsqrt_rn((float)num_d2), (double)__fsqrt_rn((float)den_d2));
+}
+
+struct RatioOut {            // optional fused ratio-test outputs of the dense kernels
+    double tau;
+    double *ratio;           // [M] or null
+    uint8_t *mask;           // [M] or null
+};
+
+__device__ __forceinline__ void write_ratio(const RatioOut &r, int64_t row, uint32_t d2a, uint32_t d2b) {
+    if (r.ratio == nullptr && r.mask == nullptr) return;
+    const double v = ratio_f32sqrt(d2a, d2b);
+    if (r.ratio) r.ratio[row] = v;
+    if (r.mask) r.mask[row] = v < r.tau ? 1 : 0;
+}
+
 __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
     return __shfl_xor_sync(0xffffffffu, v, m);
 }
@@ -67,8 +87,8 @@ int launch_sweep_mma_grouped(const uint8_t *qpool, const int32_t *q_gather, cons
                              int32_t *q2t_idx, int32_t *t2q_idx, uint8_t *mutual,
                              unsigned long long *colkeys, cudaStream_t s);
 int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int32_t t_index_base,
-                   uint32_t *d2, int32_t *idx, uint64_t *keys, void *ws, size_t ws_bytes,
-                   cudaStream_t s);
+                   uint32_t *d2, int32_t *idx, uint64_t *keys, RatioOut rout, void *ws,
+                   size_t ws_bytes, cudaStream_t s);
 size_t top2_tc_workspace_bytes(int64_t M, int64_t N);
 size_t grouped_tc_workspace_bytes(int64_t total_q, int64_t tpool_rows, bool gather);
 int launch_grouped_tc(const uint8_t *qpool, const int32_t *q_gather, const int64_t *q_off,

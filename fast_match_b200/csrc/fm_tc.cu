@@ -203,7 +203,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
           int ntiles_total, int splits, const int *__restrict__ qn, const int *__restrict__ ckey,
           int *__restrict__ gbound, uint32_t *__restrict__ out_d2,
           int32_t *__restrict__ out_idx, unsigned long long *__restrict__ out_keys,
-          unsigned long long *__restrict__ partial) {
+          unsigned long long *__restrict__ partial, const RatioOut rout) {
 #ifdef FM_TC_PROF
     const long long _tk0 = clock64();
     unsigned long long _pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -425,6 +425,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                     out_idx[grow * 2] = a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a;
                     out_idx[grow * 2 + 1] = b == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)b;
                     if (out_keys) { out_keys[grow * 2] = a; out_keys[grow * 2 + 1] = b; }
+                    write_ratio(rout, grow, (uint32_t)(a >> 32), (uint32_t)(b >> 32));   // fused ratio test
                 }
             }
         }
@@ -446,7 +447,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
 // merge of the per-split partial keys (same semantics as fm_merge_top2)
 __global__ void k_merge_partial(const unsigned long long *__restrict__ partial, int splits,
                                 int64_t M, uint32_t *__restrict__ d2, int32_t *__restrict__ idx,
-                                unsigned long long *__restrict__ keys) {
+                                unsigned long long *__restrict__ keys, const RatioOut rout) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= M) return;
     unsigned long long a = FM_NONE_KEY, b = FM_NONE_KEY;
@@ -460,6 +461,13 @@ __global__ void k_merge_partial(const unsigned long long *__restrict__ partial, 
     idx[2 * i] = a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a;
     idx[2 * i + 1] = b == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)b;
     if (keys) { keys[2 * i] = a; keys[2 * i + 1] = b; }
+    write_ratio(rout, i, (uint32_t)(a >> 32), (uint32_t)(b >> 32));
+}
+
+// all slots missing (no targets): the ratio test sees +inf
+__global__ void k_ratio_none(int64_t M, const RatioOut rout) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < M) write_ratio(rout, i, FM_NONE_D2, FM_NONE_D2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -540,13 +548,18 @@ size_t top2_tc_workspace_bytes(int64_t M, int64_t N) {
 }
 
 int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int32_t t_index_base,
-                   uint32_t *d2, int32_t *idx, uint64_t *keys, void *ws, size_t ws_bytes,
-                   cudaStream_t s) {
+                   uint32_t *d2, int32_t *idx, uint64_t *keys, RatioOut rout, void *ws,
+                   size_t ws_bytes, cudaStream_t s) {
     using namespace tc;
     if (N == 0) {  // nothing to match against: every slot is missing
         FM_CUDA_TRY(cudaMemsetAsync(d2, 0xFF, (size_t)M * 8, s));
         FM_CUDA_TRY(cudaMemsetAsync(idx, 0xFF, (size_t)M * 8, s));
         if (keys) FM_CUDA_TRY(cudaMemsetAsync(keys, 0xFF, (size_t)M * 16, s));
+        if (rout.ratio || rout.mask) {
+            k_ratio_none<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(M, rout);
+            FM_CUDA_TRY(cudaGetLastError());
+            count_launch();
+        }
         return FM_OK;
     }
     const Plan p = make_plan(M, N);
@@ -578,13 +591,13 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     prof_begin(s);
     k_top2_tc<<<grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base,
                                                  (int)p.ntiles, p.splits, qn, ckey, gbound, d2,
-                                                 idx, (unsigned long long *)keys, partial);
+                                                 idx, (unsigned long long *)keys, partial, rout);
     prof_end(s);
     FM_CUDA_TRY(cudaGetLastError());
     count_launch();
     if (partial) {
         k_merge_partial<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(partial, p.splits, M, d2, idx,
-                                                                    (unsigned long long *)keys);
+                                                                    (unsigned long long *)keys, rout);
         FM_CUDA_TRY(cudaGetLastError());
         count_launch();
     }

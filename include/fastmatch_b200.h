@@ -71,6 +71,16 @@ int fm_top2_u8(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int32_t
                void *stream);
 
 /*
+ * Ratio-Match in one call: exact top-2 with the Lowe ratio test fused into the kernel's
+ * write-out (Classic Matching.ipynb cell 3: knnMatch(k=2), m[0].distance / m[1].distance,
+ * compared with tau).  ratio [M] float64 and/or mask [M] uint8 (ratio < tau); one of the two
+ * may be NULL.  A query with fewer than two targets gets ratio = +inf, mask = 0.
+ */
+int fm_ratio_match_u8(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, double tau,
+                      uint32_t *d2, int32_t *idx, double *ratio, uint8_t *mask, void *ws,
+                      size_t ws_bytes, int algo, void *stream);
+
+/*
  * Ratio test on squared distances.  Replaces the Python-side arithmetic
  *   fastmatch.pyx:124 and :165  ratio = m.distance / cached_distance[queryIdx]
  *   Classic Matching.ipynb cell 3 JSON :65  ratio = m[0].distance / m[1].distance

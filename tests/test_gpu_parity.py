@@ -100,6 +100,20 @@ def test_ratio(cuda):
     assert torch.isinf(r).all() and not m.any()
 
 
+@pytest.mark.parametrize("algo", ALGOS)
+def test_ratio_match_fused(cuda, algo):
+    """fm_ratio_match_u8: top-2 with the ratio test fused into the kernel write-out."""
+    for (M, N, seed) in ((4000, 4100, 4), (20000, 30000, 5), (700, 1, 6), (300, 0, 7)):
+        q, t = synth.make_pair(M, max(N, 1), seed=seed)
+        t = t[:N]
+        od2, oidx = oracle.c_top2(q, t)
+        for tau in (0.7, 0.9):
+            d2, idx, r, m = backend.ratio_match(_dev(q, cuda), _dev(t, cuda), tau, algo=algo, want_ratio=True)
+            orr, om = oracle.np_ratio(od2[:, 0], den_d2=od2[:, 1], tau=tau)
+            assert np.array_equal(_u32(d2), od2) and np.array_equal(idx.cpu().numpy(), oidx)
+            assert np.array_equal(r.cpu().numpy(), orr) and np.array_equal(m.cpu().numpy(), om)
+
+
 def _check_grouped(qpool, q_off, tpool, t_off, cuda, q_gather=None):
     for algo in ALGOS:
         _check_grouped_algo(qpool, q_off, tpool, t_off, cuda, q_gather, algo)
