@@ -279,10 +279,21 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                     { PROF_T0(); mbar_wait(smem_u32(&bars->tmem_empty[s]), (it & 1) ^ 1); PROF_ADD(1); }
                     tc_fence_after();
                     const uint64_t adesc = make_desc(smem_u32(smem + SMEM_A + s * A_BYTES));
+#ifdef FM_EXPERIMENT_N128   /* timing experiment: the same tile as two N=128 instructions per K-step */
+                    constexpr uint32_t idesc128 = make_idesc(BM, 128);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                        for (int k = 0; k < FM_DIM / 32; ++k)
+                            umma_i8(tmem_base + s * BN + h * 128, adesc + 2 * k, bdesc + 2 * k + h * (128 * FM_DIM / 16), idesc128, k > 0);
+                        umma_i8(tmem_base + s * BN + h * 128, axdesc, bxdesc + h * (128 * 32 / 16), idesc128, 1);
+                    }
+#else
 #pragma unroll
                     for (int k = 0; k < FM_DIM / 32; ++k)
                         umma_i8(tmem_base + s * BN, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
                     umma_i8(tmem_base + s * BN, axdesc, bxdesc, idesc, 1);   // + E_j
+#endif
                     umma_commit(smem_u32(&bars->tmem_full[s]));
                 }
                 umma_commit(smem_u32(&bars->empty[stage]));
