@@ -51,7 +51,7 @@ constexpr int B_BYTES = BN * FM_DIM;    // 32 KB per stage
 constexpr int TMEM_COLS = 512;
 
 struct __align__(8) Bars {
-    unsigned long long full[STAGES], empty[STAGES], a_full, tmem_full[SUBS], tmem_empty[SUBS];
+    unsigned long long full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[SUBS], tmem_empty[SUBS];
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -142,6 +142,31 @@ __device__ unsigned long long g_prof[16];
 #define PROF_ADD(slot)
 #endif
 
+// first CTA of a `grid`-CTA launch whose work range [work*c/grid, work*(c+1)/grid) holds `step`
+__host__ __device__ __forceinline__ long long cta_of_step(long long step, long long work, long long grid) {
+    long long c = step * grid / work;
+    while (work * (c + 1) / grid <= step) ++c;
+    while (c > 0 && work * c / grid > step) --c;
+    return c;
+}
+
+// A CTA's work range as a sequence of segments: runs of target tiles of one M-block.  Only the
+// first segment can start in the middle of an M-block (and so be a later slot of it).
+struct Segments {
+    int mblock, tile_begin, remaining, slot, ntiles_row;
+    __device__ __forceinline__ bool more() const { return remaining > 0; }
+    __device__ __forceinline__ int ntiles() const {
+        const int room = ntiles_row - tile_begin;
+        return remaining < room ? remaining : room;
+    }
+    __device__ __forceinline__ void advance() {
+        remaining -= ntiles();
+        ++mblock;
+        tile_begin = 0;
+        slot = 0;
+    }
+};
+
 struct RowState {
     int m1, i1, m2, i2;   // best / second-best partial distance (|t|^2 - 2 q.t) and target index
 };
@@ -200,10 +225,9 @@ __device__ __forceinline__ void slow16(const int *v, uint32_t ck_saddr, int jtil
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
           const __grid_constant__ CUtensorMap map_x, int64_t M, int64_t N, int32_t t_index_base,
-          int ntiles_total, int splits, const int *__restrict__ qn, const int *__restrict__ ckey,
-          int *__restrict__ gbound, uint32_t *__restrict__ out_d2,
-          int32_t *__restrict__ out_idx, unsigned long long *__restrict__ out_keys,
-          unsigned long long *__restrict__ partial, const RatioOut rout) {
+          int ntiles_row, long long work_total, const int *__restrict__ qn,
+          const int *__restrict__ ckey, int *__restrict__ gbound,
+          unsigned long long *__restrict__ partial) {
 #ifdef FM_TC_PROF
     const long long _tk0 = clock64();
     unsigned long long _pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -214,14 +238,26 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     unsigned long long *skeys = (unsigned long long *)(smem + SMEM_KEYS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int mblock = blockIdx.x, split = blockIdx.y;
-    const int tile_begin = (int)((int64_t)ntiles_total * split / splits);
-    const int tile_end = (int)((int64_t)ntiles_total * (split + 1) / splits);
-    const int ntiles = tile_end - tile_begin;
+    // Persistent, stream-K style schedule: the work is the sequence of (M-block, target tile)
+    // steps in M-block-major order; this CTA owns the contiguous range [w_begin, w_end) of it, i.e.
+    // a few *segments*, each a run of tiles of one M-block.  A segment's candidates go to the
+    // partial-key slot `cta - first CTA that touches the M-block`.
+    Segments seg0;
+    {
+        const long long w_begin = work_total * blockIdx.x / gridDim.x;
+        const long long w_end = work_total * (blockIdx.x + 1) / gridDim.x;
+        seg0.ntiles_row = ntiles_row;
+        seg0.mblock = (int)(w_begin / ntiles_row);
+        seg0.tile_begin = (int)(w_begin - (long long)seg0.mblock * ntiles_row);
+        seg0.remaining = (int)(w_end - w_begin);          // < 2^31: checked by the host
+        seg0.slot = seg0.tile_begin == 0 ? 0
+            : (int)(blockIdx.x - cta_of_step(w_begin - seg0.tile_begin, work_total, gridDim.x));
+    }
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
         mbar_init(smem_u32(&bars->a_full), 1);
+        mbar_init(smem_u32(&bars->a_empty), 1);
         for (int i = 0; i < SUBS; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_WARPS / SUBS); }
         fence_barrier_init();
         tma_prefetch_desc(&map_q);
@@ -244,19 +280,31 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         // ===================== TMA producer =====================
         if (lane == 0) {
             const uint32_t abar = smem_u32(&bars->a_full);
-            mbar_expect_tx(abar, SUBS * A_BYTES);
-            for (int s = 0; s < SUBS; ++s)
-                tma_load_2d(smem_u32(smem + SMEM_A + s * A_BYTES), &map_q, 0,
-                            mblock * (SUBS * BM) + s * BM, abar);
-            for (int it = 0; it < ntiles; ++it) {
-                const int stage = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+            int u = 0;      // tiles issued by this CTA so far (ring position)
+            auto load_b = [&](int tile, int uu) {
+                const int stage = uu % STAGES;
+                const uint32_t ph = (uu / STAGES) & 1;
                 { PROF_T0(); mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1); PROF_ADD(2); }
                 const uint32_t fb = smem_u32(&bars->full[stage]);
                 mbar_expect_tx(fb, B_BYTES + BX_BYTES);
                 uint8_t *st = smem + SMEM_B + stage * STAGE_BYTES;
-                tma_load_2d(smem_u32(st), &map_t, 0, (tile_begin + it) * BN, fb);
-                tma_load_2d(smem_u32(st + B_BYTES), &map_x, 0, (tile_begin + it) * BN, fb);
+                tma_load_2d(smem_u32(st), &map_t, 0, tile * BN, fb);
+                tma_load_2d(smem_u32(st + B_BYTES), &map_x, 0, tile * BN, fb);
+            };
+            Segments sg = seg0;
+            for (int seg = 0; sg.more(); ++seg, sg.advance()) {
+                const int nt = sg.ntiles();
+                // The first target tiles of a segment only need ring slots (freed by the previous
+                // segment's MMAs), so they are requested before the single-buffered query tile,
+                // which has to wait until the previous segment's last MMA is done.
+                const int pre = nt < STAGES ? nt : STAGES;
+                for (int it = 0; it < pre; ++it, ++u) load_b(sg.tile_begin + it, u);
+                mbar_wait(smem_u32(&bars->a_empty), (seg & 1) ^ 1);
+                mbar_expect_tx(abar, SUBS * A_BYTES);
+                for (int s = 0; s < SUBS; ++s)
+                    tma_load_2d(smem_u32(smem + SMEM_A + s * A_BYTES), &map_q, 0,
+                                sg.mblock * (SUBS * BM) + s * BM, abar);
+                for (int it = pre; it < nt; ++it, ++u) load_b(sg.tile_begin + it, u);
             }
         }
     } else if (warp == 1) {
@@ -264,11 +312,15 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(BM, BN);
             const uint64_t axdesc = make_desc_sw32(smem_u32(smem + SMEM_AX));
-            mbar_wait(smem_u32(&bars->a_full), 0);
+            int u = 0;
+            Segments sg = seg0;
+            for (int seg = 0; sg.more(); ++seg, sg.advance()) {
+            mbar_wait(smem_u32(&bars->a_full), seg & 1);
             tc_fence_after();
-            for (int it = 0; it < ntiles; ++it) {
-                const int stage = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+            const int nt = sg.ntiles();
+            for (int it = 0; it < nt; ++it, ++u) {
+                const int stage = u % STAGES;
+                const uint32_t ph = (u / STAGES) & 1;
                 { PROF_T0(); mbar_wait(smem_u32(&bars->full[stage]), ph); PROF_ADD(0); }
                 tc_fence_after();
                 const uint32_t sb = smem_u32(smem + SMEM_B + stage * STAGE_BYTES);
@@ -276,7 +328,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                 const uint64_t bxdesc = make_desc_sw32(sb + B_BYTES);
 #pragma unroll
                 for (int s = 0; s < SUBS; ++s) {
-                    { PROF_T0(); mbar_wait(smem_u32(&bars->tmem_empty[s]), (it & 1) ^ 1); PROF_ADD(1); }
+                    { PROF_T0(); mbar_wait(smem_u32(&bars->tmem_empty[s]), (u & 1) ^ 1); PROF_ADD(1); }
                     tc_fence_after();
                     const uint64_t adesc = make_desc(smem_u32(smem + SMEM_A + s * A_BYTES));
 #ifdef FM_EXPERIMENT_N128   /* timing experiment: the same tile as two N=128 instructions per K-step */
@@ -298,6 +350,8 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                 }
                 umma_commit(smem_u32(&bars->empty[stage]));
             }
+            umma_commit(smem_u32(&bars->a_empty));      // the query tile may be replaced
+            }
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
@@ -312,27 +366,30 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         const int ch = (ew >> 2) & 1;        // column half
         const int row_in_sub = lq * 32 + lane;
         constexpr int cg = CG;
-        RowState st;
-        st.m1 = st.m2 = NONE_P; st.i1 = st.i2 = -1;
         // sm2[row]: (second-best partial distance + 1) published by the two warps that sweep the
         // same row (and by other CTAs, below) -- "+1" because a sibling's candidate may carry a
         // higher index (non-strict bound).
         const uint32_t sm2_a = smem_u32(smem + SMEM_M2) + (s * BM + row_in_sub) * 4;
-        if (ch == 0) st_shared_s32(sm2_a, NONE_P);
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
-
         // exact-key constants of this warp's 128 columns: warp-private, double-buffered in smem
         const uint32_t ck_a = smem_u32(smem + SMEM_CK) + ew * (2 * COLS_PER_WARP * 4);
-        const int *ckg = ckey + (int64_t)tile_begin * BN + ch * COLS_PER_WARP + lane * 4;
-        if (ntiles > 0) cp_async16(ck_a + lane * 16, ckg);
-        cp_async_commit();
         // per-warp TMEM address of its 32 lanes x 128 columns (warp-uniform)
         const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + s * BN + ch * COLS_PER_WARP, 0);
         const uint32_t full_a = smem_u32(&bars->tmem_full[s]), empty_a = smem_u32(&bars->tmem_empty[s]);
+        int u = 0;          // tiles consumed by this CTA so far (barrier phase)
+        for (Segments sg = seg0; sg.more(); sg.advance()) {
+        const int mblock = sg.mblock, tile_begin = sg.tile_begin, ntiles = sg.ntiles();
+        RowState st;
+        st.m1 = st.m2 = NONE_P; st.i1 = st.i2 = -1;
+        if (ch == 0) st_shared_s32(sm2_a, NONE_P);
+        // (also orders the previous segment's reads of the exchange area before this segment's writes)
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+        const int *ckg = ckey + (int64_t)tile_begin * BN + ch * COLS_PER_WARP + lane * 4;
+        cp_async16(ck_a + lane * 16, ckg);
+        cp_async_commit();
         const int64_t grow = (int64_t)mblock * (SUBS * BM) + s * BM + row_in_sub;
         int gnext = NONE_P, gpub = NONE_P;
 
-        for (int it = 0; it < ntiles; ++it) {
+        for (int it = 0; it < ntiles; ++it, ++u) {
             const int jtile = (tile_begin + it) * BN;
             if (it + 1 < ntiles)
                 cp_async16(ck_a + ((it + 1) & 1) * (COLS_PER_WARP * 4) + lane * 16, ckg + (int64_t)(it + 1) * BN);
@@ -356,7 +413,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
 #ifdef FM_TC_PROF
             const long long _te0 = clock64();
 #endif
-            mbar_wait(full_a, it & 1);
+            mbar_wait(full_a, u & 1);
 #ifdef FM_TC_PROF
             const long long _te1 = clock64();
 #endif
@@ -427,19 +484,11 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
             unsigned long long a = skeys[r * 4], b = skeys[r * 4 + 1];
             merge2(a, b, skeys[r * 4 + 2], skeys[r * 4 + 3]);
             if (grow < M) {
-                if (partial) {
-                    partial[((int64_t)split * M + grow) * 2] = a;
-                    partial[((int64_t)split * M + grow) * 2 + 1] = b;
-                } else {
-                    out_d2[grow * 2] = (uint32_t)(a >> 32);
-                    out_d2[grow * 2 + 1] = (uint32_t)(b >> 32);
-                    out_idx[grow * 2] = a == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)a;
-                    out_idx[grow * 2 + 1] = b == FM_NONE_KEY ? -1 : (int32_t)(uint32_t)b;
-                    if (out_keys) { out_keys[grow * 2] = a; out_keys[grow * 2 + 1] = b; }
-                    write_ratio(rout, grow, (uint32_t)(a >> 32), (uint32_t)(b >> 32));   // fused ratio test
-                }
+                partial[((int64_t)sg.slot * M + grow) * 2] = a;
+                partial[((int64_t)sg.slot * M + grow) * 2 + 1] = b;
             }
         }
+        }   // segments
     }
 
     tc_fence_before();
@@ -447,7 +496,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
 #ifdef FM_TC_PROF
     if ((threadIdx.x & 31) == 0)
         for (int i = 0; i < 8; ++i) if (_pacc[i]) atomicAdd(&g_prof[i], _pacc[i]);
-    if (threadIdx.x == 0) { atomicAdd(&g_prof[8], (unsigned long long)(clock64() - _tk0)); atomicAdd(&g_prof[9], 1ull); atomicAdd(&g_prof[10], (unsigned long long)ntiles); }
+    if (threadIdx.x == 0) { atomicAdd(&g_prof[8], (unsigned long long)(clock64() - _tk0)); atomicAdd(&g_prof[9], 1ull); atomicAdd(&g_prof[10], (unsigned long long)seg0.remaining); }
 #endif
     if (warp == 2) {
         tc_fence_after();
@@ -455,14 +504,19 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     }
 }
 
-// merge of the per-split partial keys (same semantics as fm_merge_top2)
-__global__ void k_merge_partial(const unsigned long long *__restrict__ partial, int splits,
-                                int64_t M, uint32_t *__restrict__ d2, int32_t *__restrict__ idx,
+// merge of the partial keys the CTAs that swept one M-block left in its slots (same semantics as
+// fm_merge_top2); the slot count of a block follows from the schedule.
+__global__ void k_merge_partial(const unsigned long long *__restrict__ partial, int ntiles_row,
+                                long long work_total, int grid, int64_t M,
+                                uint32_t *__restrict__ d2, int32_t *__restrict__ idx,
                                 unsigned long long *__restrict__ keys, const RatioOut rout) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= M) return;
+    const long long first = (i / (SUBS * BM)) * ntiles_row;
+    const int slots = (int)(cta_of_step(first + ntiles_row - 1, work_total, grid) -
+                            cta_of_step(first, work_total, grid)) + 1;
     unsigned long long a = FM_NONE_KEY, b = FM_NONE_KEY;
-    for (int s = 0; s < splits; ++s) {
+    for (int s = 0; s < slots; ++s) {
         const ulonglong2 v = *(const ulonglong2 *)(partial + ((int64_t)s * M + i) * 2);
         insert2(v.x, a, b);
         insert2(v.y, a, b);
@@ -485,9 +539,9 @@ __global__ void k_ratio_none(int64_t M, const RatioOut rout) {
 // host side
 // ---------------------------------------------------------------------------------------------
 struct Plan {
-    int64_t mblocks, ntiles, npad;
-    int splits;
-    size_t off_tn, off_ckey, off_digits, off_scal, off_qn, off_gbound, off_partial, total;
+    int64_t mblocks, ntiles, npad, work;
+    int grid, slots;
+    size_t off_ckey, off_digits, off_qn, off_gbound, off_partial, total;
 };
 
 static int sm_count() {
@@ -506,28 +560,22 @@ static Plan make_plan(int64_t M, int64_t N) {
     p.mblocks = (M + SUBS * BM - 1) / (SUBS * BM);
     p.ntiles = (N + BN - 1) / BN;
     p.npad = p.ntiles * BN;
-    // choose the number of target slices that minimises (waves x tiles per CTA)
+    // persistent grid: every CTA gets an equal, contiguous share of the (M-block, tile) steps
+    p.work = p.mblocks * p.ntiles;
     const int sms = sm_count();
-    int best = 1;
-    double best_cost = 1e300;
-    const int smax = (int)(p.ntiles < 32 ? (p.ntiles > 0 ? p.ntiles : 1) : 32);
-    for (int s = 1; s <= smax; ++s) {
-        const int64_t ctas = p.mblocks * s;
-        const int64_t waves = (ctas + sms - 1) / sms;
-        const double per_cta = (double)((p.ntiles + s - 1) / s) + 6.0;  // + fixed set-up, in tile units
-        const double cost = waves * per_cta;
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
-    }
-    p.splits = best;
+    p.grid = (int)(p.work < sms ? p.work : sms);
+    if (p.grid < 1) p.grid = 1;
+    const int64_t per_cta = p.work / p.grid;                     // >= 1: the shortest range
+    int64_t slots = (p.ntiles + per_cta - 1) / per_cta + 1;      // CTAs that can touch one M-block
+    if (slots > p.grid) slots = p.grid;
+    p.slots = (int)slots;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    p.off_tn = 0;
-    p.off_ckey = up(p.off_tn + (size_t)p.npad * 4);
+    p.off_ckey = 0;
     p.off_digits = up(p.off_ckey + (size_t)p.npad * 4);
-    p.off_scal = up(p.off_digits + (size_t)p.npad * 32);        // [0] = min |t|^2, [1] = C
-    p.off_qn = up(p.off_scal + 256);
+    p.off_qn = up(p.off_digits + (size_t)p.npad * 32);
     p.off_gbound = up(p.off_qn + (size_t)p.mblocks * SUBS * BM * 4);
     p.off_partial = up(p.off_gbound + (size_t)p.mblocks * SUBS * BM * 4);
-    p.total = up(p.off_partial + (p.splits > 1 ? (size_t)p.splits * M * 16 : 0));
+    p.total = up(p.off_partial + (size_t)p.slots * M * 16);
     return p;
 }
 
@@ -575,10 +623,11 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     }
     const Plan p = make_plan(M, N);
     if (ws_bytes < p.total) { set_error("tcgen05 path: workspace too small"); return FM_ENOSPACE; }
+    if (p.work / p.grid >= (int64_t)0x7FFFFFF0) { set_error("tcgen05 path: M x N too large for one launch, shard it"); return FM_EINVAL; }
     uint8_t *w = (uint8_t *)ws;
     int *ckey = (int *)(w + p.off_ckey), *qn = (int *)(w + p.off_qn);
     uint8_t *digits = w + p.off_digits;
-    unsigned long long *partial = p.splits > 1 ? (unsigned long long *)(w + p.off_partial) : nullptr;
+    unsigned long long *partial = (unsigned long long *)(w + p.off_partial);
 
     CUtensorMap map_q, map_t, map_x;
     int rc;
@@ -587,7 +636,7 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     if ((rc = make_map(&map_x, digits, N, 32, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) != FM_OK) return rc;
 
     const int64_t mpad = p.mblocks * SUBS * BM;
-    int *gbound = p.splits > 1 ? (int *)(w + p.off_gbound) : nullptr;
+    int *gbound = p.slots > 1 ? (int *)(w + p.off_gbound) : nullptr;
     k_prepass<<<(unsigned)(((mpad + p.npad) * 8 + 255) / 256), 256, 0, s>>>(q, M, mpad, t, N, p.npad, qn,
                                                                             gbound, ckey, (uint4 *)digits);
     FM_CUDA_TRY(cudaGetLastError());
@@ -598,20 +647,17 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
         FM_CUDA_TRY(cudaFuncSetAttribute(k_top2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
         attr_set = true;
     }
-    dim3 grid((unsigned)p.mblocks, (unsigned)p.splits);
     prof_begin(s);
-    k_top2_tc<<<grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base,
-                                                 (int)p.ntiles, p.splits, qn, ckey, gbound, d2,
-                                                 idx, (unsigned long long *)keys, partial, rout);
+    k_top2_tc<<<p.grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base, (int)p.ntiles,
+                                                   (long long)p.work, qn, ckey, gbound, partial);
     prof_end(s);
     FM_CUDA_TRY(cudaGetLastError());
     count_launch();
-    if (partial) {
-        k_merge_partial<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(partial, p.splits, M, d2, idx,
-                                                                    (unsigned long long *)keys, rout);
-        FM_CUDA_TRY(cudaGetLastError());
-        count_launch();
-    }
+    k_merge_partial<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(partial, (int)p.ntiles, (long long)p.work,
+                                                                p.grid, M, d2, idx,
+                                                                (unsigned long long *)keys, rout);
+    FM_CUDA_TRY(cudaGetLastError());
+    count_launch();
     return FM_OK;
 }
 
