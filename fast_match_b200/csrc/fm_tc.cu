@@ -51,7 +51,7 @@ constexpr int B_BYTES = BN * FM_DIM;    // 32 KB per stage
 constexpr int TMEM_COLS = 512;
 
 struct __align__(8) Bars {
-    unsigned long long full[STAGES], empty[STAGES], a_full, a_empty, tmem_full[SUBS], tmem_empty[SUBS];
+    unsigned long long full[8], empty[8], a_full, a_empty, tmem_full[4], tmem_empty[4];
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -222,12 +222,34 @@ __device__ __forceinline__ void slow16(const int *v, uint32_t ck_saddr, int jtil
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
-k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
-          const __grid_constant__ CUtensorMap map_x, int64_t M, int64_t N, int32_t t_index_base,
-          int ntiles_row, long long work_total, const int *__restrict__ qn,
-          const int *__restrict__ ckey, int *__restrict__ gbound,
-          unsigned long long *__restrict__ partial) {
+// PAIR = false: one CTA per work range, M = 128 MMAs, two 256-column accumulators (one per
+//                sub-tile), 4-stage ring of 256-target tiles.
+// PAIR = true:  a cluster of two CTAs (one TPC) per work range.  The leader issues M = 256,
+//                N = 128 MMAs (cta_group::2): each CTA contributes its own 128 query rows per
+//                sub-tile and half of the 128 target rows, and receives a 128 x 128 accumulator.
+//                That gives four accumulator buffers per CTA (sub-tile x column half) at the
+//                shared-memory operand traffic of the N = 256 single-CTA instruction, so the
+//                epilogue warps hold a buffer only while they read it.
+template <bool PAIR>
+struct Cfg {
+    static constexpr int NBUF = PAIR ? 4 : 2;                       // TMEM accumulator buffers
+    static constexpr int STAGES = PAIR ? 8 : 4;
+    static constexpr int STAGE_BYTES = PAIR ? (B_BYTES + BX_BYTES) / 2 : (B_BYTES + BX_BYTES);
+    static constexpr int MBLOCK_ROWS = PAIR ? 2 * SUBS * BM : SUBS * BM;
+    static constexpr int HALF_B = 64 * FM_DIM;                      // PAIR: 64 target rows per column half
+    static constexpr int HALF_X = 64 * 32;
+};
+static_assert(Cfg<true>::STAGES * Cfg<true>::STAGE_BYTES == STAGES * STAGE_BYTES, "same ring size");
+static_assert(Cfg<true>::STAGES <= 8 && STAGES <= 8, "Bars holds 8 ring slots");
+
+template <bool PAIR>
+__device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUtensorMap &map_t,
+                                            const CUtensorMap &map_x, int64_t M, int64_t N,
+                                            int32_t t_index_base, int ntiles_row, long long work_total,
+                                            const int *__restrict__ qn, const int *__restrict__ ckey,
+                                            int *__restrict__ gbound,
+                                            unsigned long long *__restrict__ partial) {
+    using C = Cfg<PAIR>;
 #ifdef FM_TC_PROF
     const long long _tk0 = clock64();
     unsigned long long _pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -238,33 +260,43 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     unsigned long long *skeys = (unsigned long long *)(smem + SMEM_KEYS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;        // 0 = leader (issues the MMAs)
     // Persistent, stream-K style schedule: the work is the sequence of (M-block, target tile)
-    // steps in M-block-major order; this CTA owns the contiguous range [w_begin, w_end) of it, i.e.
-    // a few *segments*, each a run of tiles of one M-block.  A segment's candidates go to the
-    // partial-key slot `cta - first CTA that touches the M-block`.
+    // steps in M-block-major order; a worker (CTA, or CTA pair) owns a contiguous range of it,
+    // i.e. a few *segments*, each a run of tiles of one M-block.  A segment's candidates go to
+    // the partial-key slot `worker - first worker that touches the M-block`.
+    const unsigned worker = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+    const unsigned nworkers = PAIR ? gridDim.x >> 1 : gridDim.x;
     Segments seg0;
     {
-        const long long w_begin = work_total * blockIdx.x / gridDim.x;
-        const long long w_end = work_total * (blockIdx.x + 1) / gridDim.x;
+        const long long w_begin = work_total * worker / nworkers;
+        const long long w_end = work_total * (worker + 1) / nworkers;
         seg0.ntiles_row = ntiles_row;
         seg0.mblock = (int)(w_begin / ntiles_row);
         seg0.tile_begin = (int)(w_begin - (long long)seg0.mblock * ntiles_row);
         seg0.remaining = (int)(w_end - w_begin);          // < 2^31: checked by the host
         seg0.slot = seg0.tile_begin == 0 ? 0
-            : (int)(blockIdx.x - cta_of_step(w_begin - seg0.tile_begin, work_total, gridDim.x));
+            : (int)(worker - cta_of_step(w_begin - seg0.tile_begin, work_total, nworkers));
     }
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+        for (int i = 0; i < C::STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
         mbar_init(smem_u32(&bars->a_full), 1);
         mbar_init(smem_u32(&bars->a_empty), 1);
-        for (int i = 0; i < SUBS; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_WARPS / SUBS); }
+        for (int i = 0; i < C::NBUF; ++i) {
+            mbar_init(smem_u32(&bars->tmem_full[i]), 1);
+            // 8 epilogue warps release a buffer: one group here, or 4 warps in each CTA of the pair
+            mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_WARPS / SUBS);
+        }
         fence_barrier_init();
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_t);
         tma_prefetch_desc(&map_x);
     }
-    if (warp == 2) tmem_alloc(smem_u32(&bars->tmem_base), TMEM_COLS);
+    if (warp == 2) {
+        if (PAIR) tmem_alloc_pair(smem_u32(&bars->tmem_base), TMEM_COLS);
+        else tmem_alloc(smem_u32(&bars->tmem_base), TMEM_COLS);
+    }
     if (threadIdx.x >= 128 && threadIdx.x < 128 + (AX_BYTES / 16)) {
         // constant query-side block of the norm K-step: weights 255 (x15), 1 in both 16-B halves
         *(uint4 *)(smem + SMEM_AX + (threadIdx.x - 128) * 16) =
@@ -272,98 +304,131 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         fence_proxy_async();
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();      // the peer's barriers must exist before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            const uint32_t abar = smem_u32(&bars->a_full);
-            int u = 0;      // tiles issued by this CTA so far (ring position)
+            // PAIR: both CTAs load (their own query rows, their half of every target tile) and
+            // every load signals the leader's barrier, which expects the bytes of both.
+            const uint32_t abar = PAIR ? mapa_rank(smem_u32(&bars->a_full), 0) : smem_u32(&bars->a_full);
+            int u = 0;      // tiles issued so far (ring position)
             auto load_b = [&](int tile, int uu) {
-                const int stage = uu % STAGES;
-                const uint32_t ph = (uu / STAGES) & 1;
+                const int stage = uu % C::STAGES;
+                const uint32_t ph = (uu / C::STAGES) & 1;
                 { PROF_T0(); mbar_wait(smem_u32(&bars->empty[stage]), ph ^ 1); PROF_ADD(2); }
-                const uint32_t fb = smem_u32(&bars->full[stage]);
-                mbar_expect_tx(fb, B_BYTES + BX_BYTES);
-                uint8_t *st = smem + SMEM_B + stage * STAGE_BYTES;
-                tma_load_2d(smem_u32(st), &map_t, 0, tile * BN, fb);
-                tma_load_2d(smem_u32(st + B_BYTES), &map_x, 0, tile * BN, fb);
+                const uint32_t fb_local = smem_u32(&bars->full[stage]);
+                uint8_t *st = smem + SMEM_B + stage * C::STAGE_BYTES;
+                if (PAIR) {
+                    if (rank == 0) mbar_expect_tx(fb_local, 2 * C::STAGE_BYTES);
+                    const uint32_t fb = mapa_rank(fb_local, 0);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        // column half h of the tile = targets [h*128, h*128+128): 64 from each CTA
+                        const int row = tile * BN + h * COLS_PER_WARP + (int)rank * 64;
+                        tma_load_2d_pair(smem_u32(st + h * C::HALF_B), &map_t, 0, row, fb);
+                        tma_load_2d_pair(smem_u32(st + 2 * C::HALF_B + h * C::HALF_X), &map_x, 0, row, fb);
+                    }
+                } else {
+                    mbar_expect_tx(fb_local, B_BYTES + BX_BYTES);
+                    tma_load_2d(smem_u32(st), &map_t, 0, tile * BN, fb_local);
+                    tma_load_2d(smem_u32(st + B_BYTES), &map_x, 0, tile * BN, fb_local);
+                }
             };
             Segments sg = seg0;
-            for (int seg = 0; sg.more(); ++seg, sg.advance()) {
+            int seg = 0;
+            for (; sg.more(); ++seg, sg.advance()) {
                 const int nt = sg.ntiles();
                 // The first target tiles of a segment only need ring slots (freed by the previous
                 // segment's MMAs), so they are requested before the single-buffered query tile,
                 // which has to wait until the previous segment's last MMA is done.
-                const int pre = nt < STAGES ? nt : STAGES;
+                const int pre = nt < C::STAGES ? nt : C::STAGES;
                 for (int it = 0; it < pre; ++it, ++u) load_b(sg.tile_begin + it, u);
                 mbar_wait(smem_u32(&bars->a_empty), (seg & 1) ^ 1);
-                mbar_expect_tx(abar, SUBS * A_BYTES);
-                for (int s = 0; s < SUBS; ++s)
-                    tma_load_2d(smem_u32(smem + SMEM_A + s * A_BYTES), &map_q, 0,
-                                sg.mblock * (SUBS * BM) + s * BM, abar);
+                if (PAIR) {
+                    if (rank == 0) mbar_expect_tx(smem_u32(&bars->a_full), 2 * SUBS * A_BYTES);
+                    for (int s = 0; s < SUBS; ++s)
+                        tma_load_2d_pair(smem_u32(smem + SMEM_A + s * A_BYTES), &map_q, 0,
+                                         sg.mblock * C::MBLOCK_ROWS + s * (2 * BM) + (int)rank * BM, abar);
+                } else {
+                    mbar_expect_tx(abar, SUBS * A_BYTES);
+                    for (int s = 0; s < SUBS; ++s)
+                        tma_load_2d(smem_u32(smem + SMEM_A + s * A_BYTES), &map_q, 0,
+                                    sg.mblock * C::MBLOCK_ROWS + s * BM, abar);
+                }
                 for (int it = pre; it < nt; ++it, ++u) load_b(sg.tile_begin + it, u);
             }
+            // tail: the last thing the MMA warp commits is a_empty of the last segment; once it is
+            // here, no multicast arrive is still on its way to this CTA's barriers
+            if (PAIR) mbar_wait(smem_u32(&bars->a_empty), (seg & 1) ^ 1);
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(BM, BN);
-            const uint64_t axdesc = make_desc_sw32(smem_u32(smem + SMEM_AX));
+        // ===================== MMA issuer (PAIR: the leader CTA only) =====================
+        // The whole warp walks the loop (so every address below is warp-uniform and lives in
+        // uniform registers); one elected lane issues.  The issue path must stay short: with
+        // four busy epilogue warps on the same scheduler a long one cannot keep up with 64-clk MMAs.
+        if (rank == 0) {
+            constexpr uint32_t idesc = PAIR ? make_idesc(2 * BM, COLS_PER_WARP) : make_idesc(BM, BN);
+            const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+            const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint64_t axdesc = make_desc_sw32(sbase + SMEM_AX);
+            const uint64_t adesc0 = make_desc(sbase + SMEM_A);
+            auto commit = [&](uint32_t bar) { if (PAIR) umma_commit_pair(bar); else umma_commit(bar); };
             int u = 0;
             Segments sg = seg0;
             for (int seg = 0; sg.more(); ++seg, sg.advance()) {
-            mbar_wait(smem_u32(&bars->a_full), seg & 1);
-            tc_fence_after();
-            const int nt = sg.ntiles();
-            for (int it = 0; it < nt; ++it, ++u) {
-                const int stage = u % STAGES;
-                const uint32_t ph = (u / STAGES) & 1;
-                { PROF_T0(); mbar_wait(smem_u32(&bars->full[stage]), ph); PROF_ADD(0); }
+                mbar_wait(smem_u32(&bars->a_full), seg & 1);
                 tc_fence_after();
-                const uint32_t sb = smem_u32(smem + SMEM_B + stage * STAGE_BYTES);
-                const uint64_t bdesc = make_desc(sb);
-                const uint64_t bxdesc = make_desc_sw32(sb + B_BYTES);
-#pragma unroll
-                for (int s = 0; s < SUBS; ++s) {
-                    { PROF_T0(); mbar_wait(smem_u32(&bars->tmem_empty[s]), (u & 1) ^ 1); PROF_ADD(1); }
+                const int nt = sg.ntiles();
+                for (int it = 0; it < nt; ++it, ++u) {
+                    const int stage = u % C::STAGES;
+                    const uint32_t ph = (u / C::STAGES) & 1;
+                    { PROF_T0(); mbar_wait(smem_u32(&bars->full[stage]), ph); PROF_ADD(0); }
                     tc_fence_after();
-                    const uint64_t adesc = make_desc(smem_u32(smem + SMEM_A + s * A_BYTES));
-#ifdef FM_EXPERIMENT_N128   /* timing experiment: the same tile as two N=128 instructions per K-step */
-                    constexpr uint32_t idesc128 = make_idesc(BM, 128);
+                    const uint32_t sb = sbase + SMEM_B + stage * C::STAGE_BYTES;
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int b = 0; b < C::NBUF; ++b) {
+                        const int s = PAIR ? b >> 1 : b, h = PAIR ? b & 1 : 0;
+                        { PROF_T0(); mbar_wait(smem_u32(&bars->tmem_empty[b]), (u & 1) ^ 1); PROF_ADD(1); }
+                        tc_fence_after();
+                        const uint64_t adesc = adesc0 + (uint64_t)(s * (A_BYTES >> 4));
+                        const uint64_t bdesc = make_desc(PAIR ? sb + h * C::HALF_B : sb);
+                        const uint64_t bxdesc = make_desc_sw32(PAIR ? sb + 2 * C::HALF_B + h * C::HALF_X : sb + B_BYTES);
+                        const uint32_t d = tbase + s * BN + h * COLS_PER_WARP;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < FM_DIM / 32; ++k)
-                            umma_i8(tmem_base + s * BN + h * 128, adesc + 2 * k, bdesc + 2 * k + h * (128 * FM_DIM / 16), idesc128, k > 0);
-                        umma_i8(tmem_base + s * BN + h * 128, axdesc, bxdesc + h * (128 * 32 / 16), idesc128, 1);
+                            for (int k = 0; k < FM_DIM / 32; ++k) {
+                                if (PAIR) umma_i8_pair(d, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+                                else umma_i8(d, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+                            }
+                            if (PAIR) umma_i8_pair(d, axdesc, bxdesc, idesc, 1);     // + E_j
+                            else umma_i8(d, axdesc, bxdesc, idesc, 1);
+                            commit(smem_u32(&bars->tmem_full[b]));
+                        }
+                        __syncwarp();
                     }
-#else
-#pragma unroll
-                    for (int k = 0; k < FM_DIM / 32; ++k)
-                        umma_i8(tmem_base + s * BN, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
-                    umma_i8(tmem_base + s * BN, axdesc, bxdesc, idesc, 1);   // + E_j
-#endif
-                    umma_commit(smem_u32(&bars->tmem_full[s]));
+                    if (elect_one()) commit(smem_u32(&bars->empty[stage]));
+                    __syncwarp();
                 }
-                umma_commit(smem_u32(&bars->empty[stage]));
-            }
-            umma_commit(smem_u32(&bars->a_empty));      // the query tile may be replaced
+                if (elect_one()) commit(smem_u32(&bars->a_empty));      // the query tile may be replaced
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
-        // Two groups of 8 warps, one per sub-tile, so that the groups run half a period apart:
-        // while one group is waiting for its TMEM loads the other one keeps the integer pipe busy.
-        // Inside a group a warp owns 32 rows (its TMEM lane quarter) x 128 columns (a column
-        // half), swept in two passes of 64 columns; the accumulator goes back to the MMA warp as
-        // soon as the second pass has been read.
+        // A warp owns 32 rows (its TMEM lane quarter) x 128 columns (a column half) of one
+        // sub-tile and sweeps them in two passes of 64 columns; the accumulator goes back to the
+        // MMA warp as soon as the second pass has been read.  Without PAIR the 8 warps of a
+        // sub-tile share one 256-column buffer and the two groups run half a period apart; with
+        // PAIR every (sub-tile, column half) is a buffer of its own.
         const int ew = warp - 4;
-        const int s = ew >> 3;               // sub-tile of this warp's group
+        const int s = ew >> 3;               // sub-tile
         const int lq = warp & 3;             // TMEM lane quarter this warp may touch
         const int ch = (ew >> 2) & 1;        // column half
+        const int bi = PAIR ? s * 2 + ch : s;
         const int row_in_sub = lq * 32 + lane;
         constexpr int cg = CG;
         // sm2[row]: (second-best partial distance + 1) published by the two warps that sweep the
@@ -374,10 +439,11 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         const uint32_t ck_a = smem_u32(smem + SMEM_CK) + ew * (2 * COLS_PER_WARP * 4);
         // per-warp TMEM address of its 32 lanes x 128 columns (warp-uniform)
         const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + s * BN + ch * COLS_PER_WARP, 0);
-        const uint32_t full_a = smem_u32(&bars->tmem_full[s]), empty_a = smem_u32(&bars->tmem_empty[s]);
-        int u = 0;          // tiles consumed by this CTA so far (barrier phase)
+        const uint32_t full_a = smem_u32(&bars->tmem_full[bi]);
+        const uint32_t empty_a = PAIR ? mapa_rank(smem_u32(&bars->tmem_empty[bi]), 0) : smem_u32(&bars->tmem_empty[bi]);
+        int u = 0;          // tiles consumed so far (barrier phase)
         for (Segments sg = seg0; sg.more(); sg.advance()) {
-        const int mblock = sg.mblock, tile_begin = sg.tile_begin, ntiles = sg.ntiles();
+        const int tile_begin = sg.tile_begin, ntiles = sg.ntiles();
         RowState st;
         st.m1 = st.m2 = NONE_P; st.i1 = st.i2 = -1;
         if (ch == 0) st_shared_s32(sm2_a, NONE_P);
@@ -386,7 +452,8 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
         const int *ckg = ckey + (int64_t)tile_begin * BN + ch * COLS_PER_WARP + lane * 4;
         cp_async16(ck_a + lane * 16, ckg);
         cp_async_commit();
-        const int64_t grow = (int64_t)mblock * (SUBS * BM) + s * BM + row_in_sub;
+        const int64_t grow = (int64_t)sg.mblock * C::MBLOCK_ROWS +
+                             (PAIR ? s * (2 * BM) + (int)rank * BM : s * BM) + row_in_sub;
         int gnext = NONE_P, gpub = NONE_P;
 
         for (int it = 0; it < ntiles; ++it, ++u) {
@@ -431,7 +498,7 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
                 if (pass == 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(empty_a);
+                    if (lane == 0) { if (PAIR) mbar_arrive_cluster(empty_a); else mbar_arrive(empty_a); }
                 }
 #ifdef FM_EXPERIMENT_NO_SLOW   /* timing experiment only: results are wrong */
 #define FM_TRIG(x) ((x) > 0x7FFFFFF0)
@@ -492,7 +559,10 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
     }
 
     tc_fence_before();
-    __syncthreads();
+    // PAIR: neither CTA may leave (or free its TMEM) while the peer can still signal its barriers
+    // or the tensor core can still read its shared memory
+    if (PAIR) cluster_sync_all();
+    else __syncthreads();
 #ifdef FM_TC_PROF
     if ((threadIdx.x & 31) == 0)
         for (int i = 0; i < 8; ++i) if (_pacc[i]) atomicAdd(&g_prof[i], _pacc[i]);
@@ -500,19 +570,38 @@ k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUt
 #endif
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
+          const __grid_constant__ CUtensorMap map_x, int64_t M, int64_t N, int32_t t_index_base,
+          int ntiles_row, long long work_total, const int *__restrict__ qn,
+          const int *__restrict__ ckey, int *__restrict__ gbound,
+          unsigned long long *__restrict__ partial) {
+    k_top2_body<false>(map_q, map_t, map_x, M, N, t_index_base, ntiles_row, work_total, qn, ckey, gbound, partial);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+k_top2_tc_pair(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
+               const __grid_constant__ CUtensorMap map_x, int64_t M, int64_t N, int32_t t_index_base,
+               int ntiles_row, long long work_total, const int *__restrict__ qn,
+               const int *__restrict__ ckey, int *__restrict__ gbound,
+               unsigned long long *__restrict__ partial) {
+    k_top2_body<true>(map_q, map_t, map_x, M, N, t_index_base, ntiles_row, work_total, qn, ckey, gbound, partial);
 }
 
 // merge of the partial keys the CTAs that swept one M-block left in its slots (same semantics as
 // fm_merge_top2); the slot count of a block follows from the schedule.
 __global__ void k_merge_partial(const unsigned long long *__restrict__ partial, int ntiles_row,
-                                long long work_total, int grid, int64_t M,
+                                long long work_total, int grid, int mblock_rows, int64_t M,
                                 uint32_t *__restrict__ d2, int32_t *__restrict__ idx,
                                 unsigned long long *__restrict__ keys, const RatioOut rout) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= M) return;
-    const long long first = (i / (SUBS * BM)) * ntiles_row;
+    const long long first = (i / mblock_rows) * ntiles_row;
     const int slots = (int)(cta_of_step(first + ntiles_row - 1, work_total, grid) -
                             cta_of_step(first, work_total, grid)) + 1;
     unsigned long long a = FM_NONE_KEY, b = FM_NONE_KEY;
@@ -539,8 +628,10 @@ __global__ void k_ratio_none(int64_t M, const RatioOut rout) {
 // host side
 // ---------------------------------------------------------------------------------------------
 struct Plan {
-    int64_t mblocks, ntiles, npad, work;
-    int grid, slots;
+    bool pair;                  // CTA-pair kernel (cta_group::2)
+    int mblock_rows;            // query rows per M-block: 256, or 512 for a pair
+    int64_t mblocks, mpad, ntiles, npad, work;
+    int workers, slots;         // CTAs (or pairs) in the persistent grid; partial-key slots per row
     size_t off_ckey, off_digits, off_qn, off_gbound, off_partial, total;
 };
 
@@ -555,26 +646,41 @@ static int sm_count() {
     return n;
 }
 
+// FM_TC_PAIR=0 / 1 forces the single-CTA / CTA-pair kernel (for A/B timing); default: pair
+// whenever a 512-row M-block is not mostly padding.
+static int pair_override() {
+    static int v = -2;
+    if (v == -2) {
+        const char *e = getenv("FM_TC_PAIR");
+        v = e && *e ? atoi(e) : -1;
+    }
+    return v;
+}
+
 static Plan make_plan(int64_t M, int64_t N) {
     Plan p;
-    p.mblocks = (M + SUBS * BM - 1) / (SUBS * BM);
+    const int ov = pair_override();
+    p.pair = ov >= 0 ? ov != 0 : M > SUBS * BM;
+    p.mblock_rows = p.pair ? 2 * SUBS * BM : SUBS * BM;
+    p.mblocks = (M + p.mblock_rows - 1) / p.mblock_rows;
+    p.mpad = p.mblocks * p.mblock_rows;
     p.ntiles = (N + BN - 1) / BN;
     p.npad = p.ntiles * BN;
-    // persistent grid: every CTA gets an equal, contiguous share of the (M-block, tile) steps
+    // persistent grid: every worker gets an equal, contiguous share of the (M-block, tile) steps
     p.work = p.mblocks * p.ntiles;
-    const int sms = sm_count();
-    p.grid = (int)(p.work < sms ? p.work : sms);
-    if (p.grid < 1) p.grid = 1;
-    const int64_t per_cta = p.work / p.grid;                     // >= 1: the shortest range
-    int64_t slots = (p.ntiles + per_cta - 1) / per_cta + 1;      // CTAs that can touch one M-block
-    if (slots > p.grid) slots = p.grid;
+    const int cap = p.pair ? sm_count() / 2 : sm_count();
+    p.workers = (int)(p.work < cap ? p.work : cap);
+    if (p.workers < 1) p.workers = 1;
+    const int64_t per_worker = p.work / p.workers;               // >= 1: the shortest range
+    int64_t slots = (p.ntiles + per_worker - 1) / per_worker + 1;  // workers that can touch one M-block
+    if (slots > p.workers) slots = p.workers;
     p.slots = (int)slots;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     p.off_ckey = 0;
     p.off_digits = up(p.off_ckey + (size_t)p.npad * 4);
     p.off_qn = up(p.off_digits + (size_t)p.npad * 32);
-    p.off_gbound = up(p.off_qn + (size_t)p.mblocks * SUBS * BM * 4);
-    p.off_partial = up(p.off_gbound + (size_t)p.mblocks * SUBS * BM * 4);
+    p.off_gbound = up(p.off_qn + (size_t)p.mpad * 4);
+    p.off_partial = up(p.off_gbound + (size_t)p.mpad * 4);
     p.total = up(p.off_partial + (size_t)p.slots * M * 16);
     return p;
 }
@@ -623,38 +729,45 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     }
     const Plan p = make_plan(M, N);
     if (ws_bytes < p.total) { set_error("tcgen05 path: workspace too small"); return FM_ENOSPACE; }
-    if (p.work / p.grid >= (int64_t)0x7FFFFFF0) { set_error("tcgen05 path: M x N too large for one launch, shard it"); return FM_EINVAL; }
+    if (p.work / p.workers >= (int64_t)0x7FFFFFF0) { set_error("tcgen05 path: M x N too large for one launch, shard it"); return FM_EINVAL; }
     uint8_t *w = (uint8_t *)ws;
     int *ckey = (int *)(w + p.off_ckey), *qn = (int *)(w + p.off_qn);
     uint8_t *digits = w + p.off_digits;
     unsigned long long *partial = (unsigned long long *)(w + p.off_partial);
 
+    // a pair loads every target tile as four 64-row boxes (column half x CTA)
+    const int tbox = p.pair ? 64 : BN;
     CUtensorMap map_q, map_t, map_x;
     int rc;
     if ((rc = make_map(&map_q, q, M, FM_DIM, BM, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
-    if ((rc = make_map(&map_t, t, N, FM_DIM, BN, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
-    if ((rc = make_map(&map_x, digits, N, 32, BN, CU_TENSOR_MAP_SWIZZLE_NONE)) != FM_OK) return rc;
+    if ((rc = make_map(&map_t, t, N, FM_DIM, tbox, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
+    if ((rc = make_map(&map_x, digits, N, 32, tbox, CU_TENSOR_MAP_SWIZZLE_NONE)) != FM_OK) return rc;
 
-    const int64_t mpad = p.mblocks * SUBS * BM;
     int *gbound = p.slots > 1 ? (int *)(w + p.off_gbound) : nullptr;
-    k_prepass<<<(unsigned)(((mpad + p.npad) * 8 + 255) / 256), 256, 0, s>>>(q, M, mpad, t, N, p.npad, qn,
-                                                                            gbound, ckey, (uint4 *)digits);
+    k_prepass<<<(unsigned)(((p.mpad + p.npad) * 8 + 255) / 256), 256, 0, s>>>(q, M, p.mpad, t, N, p.npad, qn,
+                                                                              gbound, ckey, (uint4 *)digits);
     FM_CUDA_TRY(cudaGetLastError());
     count_launch();
 
     static bool attr_set = false;
     if (!attr_set) {
         FM_CUDA_TRY(cudaFuncSetAttribute(k_top2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+        FM_CUDA_TRY(cudaFuncSetAttribute(k_top2_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
         attr_set = true;
     }
     prof_begin(s);
-    k_top2_tc<<<p.grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base, (int)p.ntiles,
-                                                   (long long)p.work, qn, ckey, gbound, partial);
+    if (p.pair)
+        k_top2_tc_pair<<<2 * p.workers, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base,
+                                                                   (int)p.ntiles, (long long)p.work, qn, ckey,
+                                                                   gbound, partial);
+    else
+        k_top2_tc<<<p.workers, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base, (int)p.ntiles,
+                                                          (long long)p.work, qn, ckey, gbound, partial);
     prof_end(s);
     FM_CUDA_TRY(cudaGetLastError());
     count_launch();
     k_merge_partial<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(partial, (int)p.ntiles, (long long)p.work,
-                                                                p.grid, M, d2, idx,
+                                                                p.workers, p.mblock_rows, M, d2, idx,
                                                                 (unsigned long long *)keys, rout);
     FM_CUDA_TRY(cudaGetLastError());
     count_launch();
