@@ -412,6 +412,9 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
                     }
                     if (elect_one()) commit(smem_u32(&bars->empty[stage]));
                     __syncwarp();
+#ifdef FM_TC_PROF
+                    if (lane == 0) atomicAdd(&g_prof[11], 1ull);
+#endif
                 }
                 if (elect_one()) commit(smem_u32(&bars->a_empty));      // the query tile may be replaced
                 __syncwarp();
@@ -495,11 +498,16 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
                 tmem_ld32(taddr0 + pass * 64 + 32, v1);
 #endif
                 tmem_ld_wait();
+#ifdef FM_EXPERIMENT_EARLY_RELEASE   /* timing experiment only (results are wrong): the accumulator goes
+                                        back before it is read, so the MMA warp never waits for the epilogue */
+                if (pass == 0 && lane == 0) { if (PAIR) mbar_arrive_cluster(empty_a); else mbar_arrive(empty_a); }
+#else
                 if (pass == 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if (PAIR) mbar_arrive_cluster(empty_a); else mbar_arrive(empty_a); }
                 }
+#endif
 #ifdef FM_EXPERIMENT_NO_SLOW   /* timing experiment only: results are wrong */
 #define FM_TRIG(x) ((x) > 0x7FFFFFF0)
 #else

@@ -86,7 +86,10 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+    // default semantics (release at CTA scope), as for the local arrive: the only thing ordered
+    // before it is this warp's TMEM reads, which tcgen05.wait::ld + fence::before_thread_sync cover.
+    // (.release.cluster would put a GPU-scope MEMBAR in front of every arrive.)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 // TMA load into this CTA's shared memory that signals a barrier which may live in the peer CTA
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1,

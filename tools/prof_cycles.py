@@ -18,6 +18,7 @@ for arg in sys.argv[1:] or ["50000"]:
     v = list(out)
     ctas, tiles = max(v[9], 1), max(v[10], 1)
     print(f"N={N} ctas={v[9]} tiles/cta={tiles/ctas:.1f} cycles/cta={v[8]/ctas:.0f} cycles/tile={v[8]/tiles:.0f}")
-    print(f"  MMA thread per tile: wait full={v[0]/tiles:.0f} wait tmem_empty={v[1]/tiles:.0f}; producer wait empty={v[2]/tiles:.0f}")
+    mt = max(v[11], 1)
+    print(f"  MMA warp per tile: wait full={v[0]/mt:.0f} wait tmem_empty={v[1]/mt:.0f}; producer wait empty={v[2]/tiles:.0f}")
     n = max(v[7], 1)
-    print(f"  epilogue per tile per warp (own sub): wait tmem_full={v[4]/n:.0f} loads+compute={v[6]/n:.0f}")
+    print(f"  epilogue per tile per warp: wait tmem_full={v[4]/n:.0f} busy={v[6]/n:.0f}")
