@@ -238,6 +238,10 @@ struct Cfg {
     static constexpr int MBLOCK_ROWS = PAIR ? 2 * SUBS * BM : SUBS * BM;
     static constexpr int HALF_B = 64 * FM_DIM;                      // PAIR: 64 target rows per column half
     static constexpr int HALF_X = 64 * 32;
+    // Who returns a ring slot to the producer: a tcgen05.commit (costs the tensor pipe a ~50 clk
+    // bubble while the epilogue reads TMEM) or the epilogue warp that sees the tile's last
+    // accumulator complete.  Measured: the second is 5 % faster without PAIR, no gain with it.
+    static constexpr bool EPILOGUE_FREES_SLOT = !PAIR;
 };
 static_assert(Cfg<true>::STAGES * Cfg<true>::STAGE_BYTES == STAGES * STAGE_BYTES, "same ring size");
 static_assert(Cfg<true>::STAGES <= 8 && STAGES <= 8, "Bars holds 8 ring slots");
@@ -406,12 +410,18 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
                             }
                             if (PAIR) umma_i8_pair(d, axdesc, bxdesc, idesc, 1);     // + E_j
                             else umma_i8(d, axdesc, bxdesc, idesc, 1);
+#ifdef FM_PAIR_COMMIT_PER_SUB   /* variant: one "accumulator ready" signal per sub-tile (both column halves) */
+                            if (!PAIR || h == 1) commit(smem_u32(&bars->tmem_full[PAIR ? s * 2 : b]));
+#else
                             commit(smem_u32(&bars->tmem_full[b]));
+#endif
                         }
                         __syncwarp();
                     }
-                    if (elect_one()) commit(smem_u32(&bars->empty[stage]));
-                    __syncwarp();
+                    if (!C::EPILOGUE_FREES_SLOT) {
+                        if (elect_one()) commit(smem_u32(&bars->empty[stage]));
+                        __syncwarp();
+                    }
 #ifdef FM_TC_PROF
                     if (lane == 0) atomicAdd(&g_prof[11], 1ull);
 #endif
@@ -433,6 +443,7 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
         const int ch = (ew >> 2) & 1;        // column half
         const int bi = PAIR ? s * 2 + ch : s;
         const int row_in_sub = lq * 32 + lane;
+        const bool releases_stage = s == SUBS - 1 && lq == 0 && (PAIR ? ch == 1 : ch == 0);
         constexpr int cg = CG;
         // sm2[row]: (second-best partial distance + 1) published by the two warps that sweep the
         // same row (and by other CTAs, below) -- "+1" because a sibling's candidate may carry a
@@ -442,7 +453,11 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
         const uint32_t ck_a = smem_u32(smem + SMEM_CK) + ew * (2 * COLS_PER_WARP * 4);
         // per-warp TMEM address of its 32 lanes x 128 columns (warp-uniform)
         const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + s * BN + ch * COLS_PER_WARP, 0);
+#ifdef FM_PAIR_COMMIT_PER_SUB
+        const uint32_t full_a = smem_u32(&bars->tmem_full[PAIR ? s * 2 : bi]);
+#else
         const uint32_t full_a = smem_u32(&bars->tmem_full[bi]);
+#endif
         const uint32_t empty_a = PAIR ? mapa_rank(smem_u32(&bars->tmem_empty[bi]), 0) : smem_u32(&bars->tmem_empty[bi]);
         int u = 0;          // tiles consumed so far (barrier phase)
         for (Segments sg = seg0; sg.more(); sg.advance()) {
@@ -488,6 +503,9 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
             const long long _te1 = clock64();
 #endif
             tc_fence_after();
+            // The last accumulator of a tile being complete means every MMA that read the tile's
+            // ring slot is done: one warp hands the slot back to the producer.
+            if (C::EPILOGUE_FREES_SLOT && releases_stage && lane == 0) mbar_arrive(smem_u32(&bars->empty[u % C::STAGES]));
             int bound = min(st.m2, shared_b);
             int thr = (cg - bound) >> 1;        // acc' > thr  <=>  C - 2 acc' < bound
 #pragma unroll
@@ -668,7 +686,8 @@ static int pair_override() {
 static Plan make_plan(int64_t M, int64_t N) {
     Plan p;
     const int ov = pair_override();
-    p.pair = ov >= 0 ? ov != 0 : M > SUBS * BM;
+    // pair by default unless its 512-row M-blocks would add a (relatively) large block of padding
+    p.pair = ov >= 0 ? ov != 0 : (M > 8 * SUBS * BM || (M > SUBS * BM && (M - 1) % (2 * SUBS * BM) >= SUBS * BM));
     p.mblock_rows = p.pair ? 2 * SUBS * BM : SUBS * BM;
     p.mblocks = (M + p.mblock_rows - 1) / p.mblock_rows;
     p.mpad = p.mblocks * p.mblock_rows;

@@ -22,7 +22,7 @@ struct Bar { unsigned long long done; uint32_t tmem; uint32_t pad; unsigned long
 // MMAs run; X5: the 5th K-step uses 32-byte-swizzle descriptors (the norm K-step of the dense kernel).
 // CMT: commit to a scratch barrier after every accumulator's K-steps (as the dense kernel does);
 // ALUW: that many extra warps run a dependent integer-max loop (issue-slot competition).
-template <bool PAIR, int N, int NACC, int MODE, int LDW = 0, bool X5 = false, bool CMT = false, int ALUW = 0, int RD_BASE = 0, int RD_SPAN = 512, int MMA_ON = 1>
+template <bool PAIR, int N, int NACC, int MODE, int LDW = 0, bool X5 = false, bool CMT = false, int ALUW = 0, int RD_BASE = 0, int RD_SPAN = 512, int MMA_ON = 1, int CMT_EVERY = 1, int LDX = 32>
 __device__ __forceinline__ void body(long long *out, int slot) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -61,7 +61,7 @@ __device__ __forceinline__ void body(long long *out, int slot) {
                     for (int a = 0; a < NACC; ++a) {
 #pragma unroll
                         for (int k = 0; k < KSTEPS; ++k) mma(a, k);
-                        if (CMT) { if (PAIR) umma_commit_pair(smem_u32(&bar->scratch[a])); else umma_commit(smem_u32(&bar->scratch[a])); }
+                        if (CMT && (a % CMT_EVERY) == CMT_EVERY - 1) { if (PAIR) umma_commit_pair(smem_u32(&bar->scratch[a])); else umma_commit(smem_u32(&bar->scratch[a])); }
                     }
                 } else {
 #pragma unroll
@@ -83,14 +83,22 @@ __device__ __forceinline__ void body(long long *out, int slot) {
         int acc = 0;
         long long nld = 0;
         while (!*stop) {
-            nld += RD_SPAN / 4 / 32;
+            nld += RD_SPAN / 4 / 32;   /* counted in 32-column units */
 #pragma unroll
-            for (int c = 0; c < RD_SPAN / 4; c += 32) {
-                int v[32];
-                tmem_ld32(taddr + c, v);
-                tmem_ld_wait();
+            for (int c = 0; c < RD_SPAN / 4; c += LDX) {
+                if (LDX == 32) {
+                    int v[32];
+                    tmem_ld32(taddr + c, v);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc ^= v[i];
+                    for (int i = 0; i < 32; ++i) acc ^= v[i];
+                } else {
+                    int v[64];
+                    tmem_ld64(taddr + c, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) acc ^= v[i];
+                }
             }
         }
         if (acc == 0x12345) out[63] = acc;
@@ -119,6 +127,8 @@ template <int N, int NACC, int MODE, int LDW = 0, bool X5 = false, bool CMT = fa
 __global__ void __launch_bounds__(640, 1) k_single(long long *out, int slot) { body<false, N, NACC, MODE, LDW, X5, CMT, ALUW>(out, slot); }
 template <bool PAIR, int N, int NACC, int RD_BASE, int RD_SPAN, int MMA_ON>
 __global__ void __launch_bounds__(640, 1) k_rd(long long *out, int slot) { body<false, N, NACC, 0, 16, false, true, 0, RD_BASE, RD_SPAN, MMA_ON>(out, slot); }
+template <int CMT_EVERY, int LDX, bool CMT>
+__global__ void __launch_bounds__(640, 1) k_cs(long long *out, int slot) { body<false, 128, 4, 0, 16, true, CMT, 0, 0, 512, 1, CMT_EVERY, LDX>(out, slot); }
 template <int N, int NACC, int MODE, int LDW = 0, bool X5 = false, bool CMT = false, int ALUW = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(640, 1) k_pair(long long *out, int slot) { body<true, N, NACC, MODE, LDW, X5, CMT, ALUW>(out, slot); }
 
@@ -146,6 +156,16 @@ int main(int argc, char **argv) {
     cudaMalloc(&d_out, 64 * 8);
     cudaMemset(d_out, 0, 64 * 8);
     int s = 0;
+    if (argc > 3) {
+        printf("-- N=128 x4 acc, 16 reader warps: commit spacing and reader load width\n");
+        run("no commits, x32 readers", k_cs<1, 32, false>, 128, 4, false, d_out, s++);
+        run("commit every acc, x32 readers", k_cs<1, 32, true>, 128, 4, false, d_out, s++);
+        run("commit every 2 acc, x32 readers", k_cs<2, 32, true>, 128, 4, false, d_out, s++);
+        run("commit every 4 acc, x32 readers", k_cs<4, 32, true>, 128, 4, false, d_out, s++);
+        run("commit every acc, x64 readers", k_cs<1, 64, true>, 128, 4, false, d_out, s++);
+        run("no commits, x64 readers", k_cs<1, 64, false>, 128, 4, false, d_out, s++);
+        return 0;
+    }
     if (argc > 2) {
         printf("-- TMEM read rate of 16 reader warps (readers on [base, base+span)) vs concurrent MMAs\n");
         run("no MMA, readers on [256,512)", k_rd<false, 256, 1, 256, 256, 0>, 256, 1, false, d_out, s++);
