@@ -335,7 +335,7 @@ def run_ours(args):
         pass
     k_ms = kern_ms / max(kern_n, 1)
     achieved = ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "k_top2_tc", "achieved": achieved, "peak": peak_tops, "unit": "TOP/s",
+    roofline = {"bound": "tensor", "kernel": "k_top2_tc_pair", "achieved": achieved, "peak": peak_tops, "unit": "TOP/s",
                 "frac": achieved / peak_tops,
                 "traffic": (traffic.get("k_top2_tc_c3_50k") or {}).get("bytes"),
                 "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json); "
