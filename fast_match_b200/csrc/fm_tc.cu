@@ -683,11 +683,31 @@ static int pair_override() {
     return v;
 }
 
+// Can a 2-CTA cluster of the pair kernel be resident at all (it cannot on e.g. a MIG slice with
+// single-SM TPCs)?  Asked once; "no" or any error selects the single-CTA kernel.
+static bool pair_available() {
+    static int ok = -1;
+    if (ok < 0) {
+        ok = 0;
+        if (cudaFuncSetAttribute(k_top2_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC) == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2);
+            cfg.blockDim = dim3(NTHREADS);
+            cfg.dynamicSmemBytes = SMEM_ALLOC;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, k_top2_tc_pair, &cfg) == cudaSuccess && n > 0) ok = 1;
+        }
+        (void)cudaGetLastError();
+    }
+    return ok == 1;
+}
+
 static Plan make_plan(int64_t M, int64_t N) {
     Plan p;
     const int ov = pair_override();
     // pair by default unless its 512-row M-blocks would add a (relatively) large block of padding
-    p.pair = ov >= 0 ? ov != 0 : (M > 8 * SUBS * BM || (M > SUBS * BM && (M - 1) % (2 * SUBS * BM) >= SUBS * BM));
+    p.pair = (ov >= 0 ? ov != 0 : (M > 8 * SUBS * BM || (M > SUBS * BM && (M - 1) % (2 * SUBS * BM) >= SUBS * BM))) &&
+             pair_available();
     p.mblock_rows = p.pair ? 2 * SUBS * BM : SUBS * BM;
     p.mblocks = (M + p.mblock_rows - 1) / p.mblock_rows;
     p.mpad = p.mblocks * p.mblock_rows;
