@@ -249,7 +249,7 @@ static_assert(Cfg<true>::STAGES <= 8 && STAGES <= 8, "Bars holds 8 ring slots");
 template <bool PAIR>
 __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUtensorMap &map_t,
                                             const CUtensorMap &map_x, int64_t M, int64_t N,
-                                            int32_t t_index_base, int ntiles_row, long long work_total,
+                                            int32_t t_index_base, int ntiles_row, long long work_total, int aligned,
                                             const int *__restrict__ qn, const int *__restrict__ ckey,
                                             int *__restrict__ gbound,
                                             unsigned long long *__restrict__ partial) {
@@ -273,8 +273,12 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
     const unsigned nworkers = PAIR ? gridDim.x >> 1 : gridDim.x;
     Segments seg0;
     {
-        const long long w_begin = work_total * worker / nworkers;
-        const long long w_end = work_total * (worker + 1) / nworkers;
+        // `aligned`: whole M-blocks per worker instead (every worker starts at tile 0 and they sweep
+        // the targets in step -- chosen by the host when the targets do not fit L2)
+        const long long units = aligned ? work_total / ntiles_row : work_total;
+        const long long scale = aligned ? ntiles_row : 1;
+        const long long w_begin = units * worker / nworkers * scale;
+        const long long w_end = units * (worker + 1) / nworkers * scale;
         seg0.ntiles_row = ntiles_row;
         seg0.mblock = (int)(w_begin / ntiles_row);
         seg0.tile_begin = (int)(w_begin - (long long)seg0.mblock * ntiles_row);
@@ -604,32 +608,32 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
           const __grid_constant__ CUtensorMap map_x, int64_t M, int64_t N, int32_t t_index_base,
-          int ntiles_row, long long work_total, const int *__restrict__ qn,
+          int ntiles_row, long long work_total, int aligned, const int *__restrict__ qn,
           const int *__restrict__ ckey, int *__restrict__ gbound,
           unsigned long long *__restrict__ partial) {
-    k_top2_body<false>(map_q, map_t, map_x, M, N, t_index_base, ntiles_row, work_total, qn, ckey, gbound, partial);
+    k_top2_body<false>(map_q, map_t, map_x, M, N, t_index_base, ntiles_row, work_total, aligned, qn, ckey, gbound, partial);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 k_top2_tc_pair(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
                const __grid_constant__ CUtensorMap map_x, int64_t M, int64_t N, int32_t t_index_base,
-               int ntiles_row, long long work_total, const int *__restrict__ qn,
+               int ntiles_row, long long work_total, int aligned, const int *__restrict__ qn,
                const int *__restrict__ ckey, int *__restrict__ gbound,
                unsigned long long *__restrict__ partial) {
-    k_top2_body<true>(map_q, map_t, map_x, M, N, t_index_base, ntiles_row, work_total, qn, ckey, gbound, partial);
+    k_top2_body<true>(map_q, map_t, map_x, M, N, t_index_base, ntiles_row, work_total, aligned, qn, ckey, gbound, partial);
 }
 
 // merge of the partial keys the CTAs that swept one M-block left in its slots (same semantics as
 // fm_merge_top2); the slot count of a block follows from the schedule.
 __global__ void k_merge_partial(const unsigned long long *__restrict__ partial, int ntiles_row,
-                                long long work_total, int grid, int mblock_rows, int64_t M,
+                                long long work_total, int grid, int aligned, int mblock_rows, int64_t M,
                                 uint32_t *__restrict__ d2, int32_t *__restrict__ idx,
                                 unsigned long long *__restrict__ keys, const RatioOut rout) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= M) return;
     const long long first = (i / mblock_rows) * ntiles_row;
-    const int slots = (int)(cta_of_step(first + ntiles_row - 1, work_total, grid) -
-                            cta_of_step(first, work_total, grid)) + 1;
+    const int slots = aligned ? 1 : (int)(cta_of_step(first + ntiles_row - 1, work_total, grid) -
+                                          cta_of_step(first, work_total, grid)) + 1;
     unsigned long long a = FM_NONE_KEY, b = FM_NONE_KEY;
     for (int s = 0; s < slots; ++s) {
         const ulonglong2 v = *(const ulonglong2 *)(partial + ((int64_t)s * M + i) * 2);
@@ -658,6 +662,7 @@ struct Plan {
     int mblock_rows;            // query rows per M-block: 256, or 512 for a pair
     int64_t mblocks, mpad, ntiles, npad, work;
     int workers, slots;         // CTAs (or pairs) in the persistent grid; partial-key slots per row
+    int aligned;                // whole M-blocks per worker (targets larger than L2)
     size_t off_ckey, off_digits, off_qn, off_gbound, off_partial, total;
 };
 
@@ -672,8 +677,20 @@ static int sm_count() {
     return n;
 }
 
-// FM_TC_PAIR=0 / 1 forces the single-CTA / CTA-pair kernel (for A/B timing); default: pair
-// whenever a 512-row M-block is not mostly padding.
+static size_t l2_bytes() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrL2CacheSize, dev);
+        if (n <= 0) n = 64 << 20;
+    }
+    return (size_t)n;
+}
+
+// FM_TC_PAIR=0 / 1 forces the single-CTA / CTA-pair kernel (for A/B timing and tests); default: pair
+// whenever a 512-row M-block is not mostly padding.  FM_TC_ALIGNED=0 / 1 likewise forces the
+// stream-K / whole-M-block schedule.
 static int pair_override() {
     static int v = -2;
     if (v == -2) {
@@ -718,10 +735,15 @@ static Plan make_plan(int64_t M, int64_t N) {
     const int cap = p.pair ? sm_count() / 2 : sm_count();
     p.workers = (int)(p.work < cap ? p.work : cap);
     if (p.workers < 1) p.workers = 1;
+    // Targets (+ digits) that do not fit L2 are streamed from HBM once per M-block unless the workers
+    // sweep them in step: give every worker whole M-blocks then (<= 1/8 imbalance by the condition).
+    static const int aligned_override = [] { const char *e = getenv("FM_TC_ALIGNED"); return e && *e ? atoi(e) : -1; }();
+    p.aligned = aligned_override >= 0 ? aligned_override != 0
+        : (size_t)p.npad * (FM_DIM + 32) > l2_bytes() / 2 && p.mblocks >= 8 * (int64_t)p.workers;
     const int64_t per_worker = p.work / p.workers;               // >= 1: the shortest range
     int64_t slots = (p.ntiles + per_worker - 1) / per_worker + 1;  // workers that can touch one M-block
     if (slots > p.workers) slots = p.workers;
-    p.slots = (int)slots;
+    p.slots = p.aligned ? 1 : (int)slots;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     p.off_ckey = 0;
     p.off_digits = up(p.off_ckey + (size_t)p.npad * 4);
@@ -805,16 +827,16 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     prof_begin(s);
     if (p.pair)
         k_top2_tc_pair<<<2 * p.workers, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base,
-                                                                   (int)p.ntiles, (long long)p.work, qn, ckey,
-                                                                   gbound, partial);
+                                                                   (int)p.ntiles, (long long)p.work, p.aligned, qn,
+                                                                   ckey, gbound, partial);
     else
         k_top2_tc<<<p.workers, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base, (int)p.ntiles,
-                                                          (long long)p.work, qn, ckey, gbound, partial);
+                                                          (long long)p.work, p.aligned, qn, ckey, gbound, partial);
     prof_end(s);
     FM_CUDA_TRY(cudaGetLastError());
     count_launch();
     k_merge_partial<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(partial, (int)p.ntiles, (long long)p.work,
-                                                                p.workers, p.mblock_rows, M, d2, idx,
+                                                                p.workers, p.aligned, p.mblock_rows, M, d2, idx,
                                                                 (unsigned long long *)keys, rout);
     FM_CUDA_TRY(cudaGetLastError());
     count_launch();
