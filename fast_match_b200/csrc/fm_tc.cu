@@ -5,17 +5,20 @@
 // u8 x u8 -> s32 contraction on tcgen05.mma kind::i8; the M x N distance matrix only ever
 // exists as TMEM accumulators.
 //
-// Work decomposition
-//   * a CTA owns an M-block of 256 query rows = two 128-row sub-tiles whose descriptors stay
-//     resident in shared memory (TMA, 128B swizzle: one descriptor = one swizzle row);
-//   * target tiles of 256 descriptors stream through a 4-stage TMA ring; every tile is
-//     multiplied against both sub-tiles, so the two 256-column TMEM accumulators ping-pong:
-//     while the epilogue drains sub-tile 0 the tensor core fills sub-tile 1;
-//   * grid = (M-blocks, N-splits): the target range is cut into `splits` slices so that the
-//     grid fills the SMs evenly; per-slice candidates are merged by a small kernel.
+// Work decomposition (details at k_top2_body)
+//   * a worker is a CTA pair (cluster of 2, one TPC; the leader issues cta_group::2 MMAs of
+//     M = 256 x N = 128) or, for small / ragged M, a single CTA (M = 128 x N = 256 MMAs);
+//   * a CTA keeps 256 query rows = two 128-row sub-tiles resident in shared memory (TMA, 128B
+//     swizzle: one descriptor = one swizzle row); target tiles of 256 descriptors stream through
+//     a TMA/mbarrier ring and every tile is multiplied against both sub-tiles;
+//   * accumulators live in TMEM: four 128-column buffers (sub-tile x column half) per CTA of a
+//     pair, two 256-column buffers in a single CTA; the epilogue drains one while the tensor core
+//     fills the others;
+//   * persistent stream-K schedule: the (M-block, tile) steps are cut into equal contiguous ranges,
+//     one per worker; a worker leaves the top-2 of each of its runs in a partial-key slot and
+//     k_merge_partial folds the slots of a row (and applies the ratio test).
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4..19 = epilogue: two groups of 8 warps, one per sub-tile (TMEM lane quarter = warp % 4,
-// column half = bit 2 of the epilogue warp index).
+// warps 4..19 = epilogue: (sub-tile, column half) x TMEM lane quarter (= warp % 4).
 //
 // The epilogue is the bottleneck (K is only 128: 512 tensor cycles per 32768 outputs, and the
 // integer min/max pipe retires 64 lanes/clk/SM), so the per-output work is ~0.5 instruction:
