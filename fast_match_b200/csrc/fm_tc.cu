@@ -768,6 +768,16 @@ extern "C" int fm_debug_prof(unsigned long long *out16, int reset) {
 }
 #endif
 
+// Test hook (not part of include/fastmatch_b200.h): the schedule the dense tcgen05 kernel would use.
+// out = {pair, mblock_rows, mblocks, ntiles, workers, slots, aligned, workspace bytes >> 10}
+extern "C" int fm_debug_plan(int64_t M, int64_t N, long long *out8) {
+    if (M <= 0 || N <= 0 || out8 == nullptr) return FM_EINVAL;
+    const tc::Plan p = tc::make_plan(M, N);
+    out8[0] = p.pair; out8[1] = p.mblock_rows; out8[2] = p.mblocks; out8[3] = p.ntiles;
+    out8[4] = p.workers; out8[5] = p.slots; out8[6] = p.aligned; out8[7] = (long long)(p.total >> 10);
+    return FM_OK;
+}
+
 bool tc_supported() {
     static int ok = -1;
     if (ok < 0) {
