@@ -243,7 +243,10 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // The whole warp walks the loop (operands stay in uniform registers), one elected lane issues.
+        {
+            const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+            const uint32_t tbase = __shfl_sync(0xffffffffu, tmem_base, 0);
             int nb[2] = {0, 0}, stops = 0;
             for (int u = 0; stops < 2; ++u) {
                 const int stage = u % STAGES;
@@ -252,7 +255,7 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 GP_T(_m1);
                 GP_ACC(3, _m0, _m1);
                 tc_fence_after();
-                const int slot_idx = bars->stage_slot[stage];
+                const int slot_idx = __shfl_sync(0xffffffffu, bars->stage_slot[stage], 0);
                 const Slot *sl = &ring[slot_idx];
                 const int buf = slot_idx / RING;
                 const int kb = nb[buf]++;
@@ -263,22 +266,30 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 GP_T(_m2);
                 GP_ACC(4, _m1, _m2);
                 tc_fence_after();
-                if (sl->flags & F_STOP) {
+                const int flags = __shfl_sync(0xffffffffu, sl->flags, 0);
+                const int n_mma = __shfl_sync(0xffffffffu, sl->n_mma, 0);
+                if (flags & F_STOP) {
                     // tcgen05.commit arrives only after every MMA issued above has completed, so the
                     // stop signal cannot overtake the accumulators still in flight
-                    umma_commit(smem_u32(&bars->tmem_full[buf]));
-                    umma_commit(smem_u32(&bars->empty[stage]));
+                    if (elect_one()) {
+                        umma_commit(smem_u32(&bars->tmem_full[buf]));
+                        umma_commit(smem_u32(&bars->empty[stage]));
+                    }
+                    __syncwarp();
                     ++stops;
                     continue;
                 }
-                const uint32_t idesc = make_idesc(BM, sl->n_mma);
-                const uint32_t sa = smem_u32(smem + SMEM_STAGES + stage * STAGE_BYTES);
+                const uint32_t idesc = make_idesc(BM, n_mma);
+                const uint32_t sa = sbase + SMEM_STAGES + stage * STAGE_BYTES;
                 const uint64_t adesc = make_desc(sa), bdesc = make_desc(sa + A_BYTES);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < FM_DIM / 32; ++k)
-                    umma_i8(tmem_base + buf * BN, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
-                umma_commit(smem_u32(&bars->tmem_full[buf]));
-                umma_commit(smem_u32(&bars->empty[stage]));
+                    for (int k = 0; k < FM_DIM / 32; ++k)
+                        umma_i8(tbase + buf * BN, adesc + 2 * k, bdesc + 2 * k, idesc, k > 0);
+                    umma_commit(smem_u32(&bars->tmem_full[buf]));
+                    umma_commit(smem_u32(&bars->empty[stage]));
+                }
+                __syncwarp();
                 GP_T(_m3);
                 GP_ACC(5, _m2, _m3);
             }
