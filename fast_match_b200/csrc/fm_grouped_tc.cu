@@ -193,8 +193,7 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             bn[k] = (!stop && c < b_valid) ? __ldg(bnorm + b_src + b0 + c) : -1;
                         }
                         GP_T(_p0);
-                        if (lane == 0) mbar_wait(smem_u32(&bars->empty[stage]), ((u / STAGES) & 1) ^ 1);
-                        __syncwarp();
+                        mbar_wait(smem_u32(&bars->empty[stage]), ((u / STAGES) & 1) ^ 1);
                         GP_T(_p1);
                         GP_ACC(0, _p0, _p1);
                         const uint32_t fb = smem_u32(&bars->full[stage]);
@@ -223,14 +222,18 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                             bars->stage_slot[stage] = slot_idx;
                         }
                         __syncwarp();
-                        if (lane == 0) mbar_expect_tx(fb, (abox + bbox) * BOX_BYTES);
+                        // 32-row boxes (only the rows the unit needs are read): up to 4 for the A slab,
+                        // up to 8 for the B rows; everything below is warp-uniform, one elected lane issues
+                        const uint32_t sa = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + SMEM_STAGES + stage * STAGE_BYTES;
+                        const int arow = (int)(a_src + a0), brow = (int)(b_src + b0);
+                        if (elect_one()) {
+                            mbar_expect_tx(fb, (abox + bbox) * BOX_BYTES);
+                            for (int i = 0; i < abox; ++i)
+                                tma_load_2d(sa + i * BOX_BYTES, amap, 0, arow + i * BOX_ROWS, fb);
+                            for (int i = 0; i < bbox; ++i)
+                                tma_load_2d(sa + A_BYTES + i * BOX_BYTES, bmap, 0, brow + i * BOX_ROWS, fb);
+                        }
                         __syncwarp();
-                        // one 32-row box per lane: lanes 0..3 the A slab, lanes 4..11 the B rows
-                        const uint32_t sa = smem_u32(smem + SMEM_STAGES + stage * STAGE_BYTES);
-                        if (lane < abox)
-                            tma_load_2d(sa + lane * BOX_BYTES, amap, 0, (int)(a_src + a0) + lane * BOX_ROWS, fb);
-                        else if (lane >= 4 && lane - 4 < bbox)
-                            tma_load_2d(sa + A_BYTES + (lane - 4) * BOX_BYTES, bmap, 0, (int)(b_src + b0) + (lane - 4) * BOX_ROWS, fb);
                         GP_T(_p2);
                         GP_ACC(1, _p1, _p2);
 #ifdef FM_TC_PROF
