@@ -303,7 +303,7 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         // quarter) x 128 columns (a column half), swept in 32-column pieces.
         const int ew = warp - 4, grp = ew >> 3, lq = warp & 3, ch = (ew >> 2) & 1;
         const int row = lq * 32 + lane;
-        const uint32_t taddr0 = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + grp * BN + ch * COLS_PER_WARP, 0);
+        const uint32_t taddr_grp = __shfl_sync(0xffffffffu, tmem_base + ((uint32_t)(lq * 32) << 16) + grp * BN, 0);
         const uint32_t full_a = smem_u32(&bars->tmem_full[grp]), empty_a = smem_u32(&bars->tmem_empty[grp]);
         int m1 = NONE_P, i1 = -1, m2 = NONE_P, i2 = -1, nslab = 0;
         for (int k = 0;; ++k) {
@@ -316,13 +316,17 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             const int flags = sl->flags;
             if (flags & F_STOP) break;
             const int b_valid = sl->b_valid, b_local0 = sl->b_local0;
-            const int ncols = min(max(b_valid - ch * COLS_PER_WARP, 0), COLS_PER_WARP);   // warp-uniform
+            // the unit's valid columns are split evenly (in 32-column pieces) between the two warps
+            // that sweep a row, so that short units do not leave the second one idle
+            const int half = ((b_valid + 63) >> 6) << 5;                                   // <= 128
+            const int ncols = ch ? max(b_valid - half, 0) : min(half, b_valid);            // warp-uniform
+            const uint32_t taddr0 = taddr_grp + ch * half;
             const bool top1 = (flags & F_PASS1) != 0;                                      // warp-uniform
             // |a_i|^2 is only needed when the slab is written out: issue the load now, use it last
             int an = 0;
             if ((flags & F_LAST) && row < sl->a_valid) an = __ldg((top1 ? P.tnorm : P.qnorm) + sl->a_row0 + row);
             if (flags & F_FIRST) { m1 = m2 = NONE_P; i1 = i2 = -1; }
-            const uint32_t cka = smem_u32(&sl->ck[ch * COLS_PER_WARP]);
+            const uint32_t cka = smem_u32(&sl->ck[0]) + ch * half * 4;
             int k1 = I32_MAX, k2 = I32_MAX;
             if (ncols == 0) {        // nothing to read: hand the accumulator back right away
                 tc_fence_before();
@@ -378,7 +382,7 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             if (ncols > 0) {
                 const int p1 = k1 >> 8;
                 if (k1 != I32_MAX && p1 < m2) {
-                    const int j1 = b_local0 + ch * COLS_PER_WARP + (k1 & 255) - ch * COLS_PER_WARP;
+                    const int j1 = b_local0 + (k1 & 255);
                     if (p1 < m1) {
                         const int p2 = k2 >> 8;
                         if (k2 != I32_MAX && p2 < m1) { m2 = p2; i2 = b_local0 + (k2 & 255); }
