@@ -347,23 +347,34 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(empty_a);
                 }
+                if (base + 32 <= ncols) {       // full piece (the common case): no per-column checks
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const int cb = base + c4 * 4;
-                    if (cb + 4 <= ncols) {
-                        const int4 ck = ld_shared_v4(cka + cb * 4);
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const int4 ck = ld_shared_v4(cka + (base + c4 * 4) * 4);
                         V[c4 * 4 + 0] = ck.x - 512 * V[c4 * 4 + 0];
                         V[c4 * 4 + 1] = ck.y - 512 * V[c4 * 4 + 1];
                         V[c4 * 4 + 2] = ck.z - 512 * V[c4 * 4 + 2];
                         V[c4 * 4 + 3] = ck.w - 512 * V[c4 * 4 + 3];
-                    } else if (cb < ncols) {
-                        const int4 ck = ld_shared_v4(cka + cb * 4);
-                        V[c4 * 4 + 0] = ck.x - 512 * V[c4 * 4 + 0];
-                        V[c4 * 4 + 1] = cb + 1 < ncols ? ck.y - 512 * V[c4 * 4 + 1] : I32_MAX;
-                        V[c4 * 4 + 2] = cb + 2 < ncols ? ck.z - 512 * V[c4 * 4 + 2] : I32_MAX;
-                        V[c4 * 4 + 3] = I32_MAX;
-                    } else {
-                        V[c4 * 4 + 0] = V[c4 * 4 + 1] = V[c4 * 4 + 2] = V[c4 * 4 + 3] = I32_MAX;
+                    }
+                } else {
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; ++c4) {
+                        const int cb = base + c4 * 4;
+                        if (cb + 4 <= ncols) {
+                            const int4 ck = ld_shared_v4(cka + cb * 4);
+                            V[c4 * 4 + 0] = ck.x - 512 * V[c4 * 4 + 0];
+                            V[c4 * 4 + 1] = ck.y - 512 * V[c4 * 4 + 1];
+                            V[c4 * 4 + 2] = ck.z - 512 * V[c4 * 4 + 2];
+                            V[c4 * 4 + 3] = ck.w - 512 * V[c4 * 4 + 3];
+                        } else if (cb < ncols) {
+                            const int4 ck = ld_shared_v4(cka + cb * 4);
+                            V[c4 * 4 + 0] = ck.x - 512 * V[c4 * 4 + 0];
+                            V[c4 * 4 + 1] = cb + 1 < ncols ? ck.y - 512 * V[c4 * 4 + 1] : I32_MAX;
+                            V[c4 * 4 + 2] = cb + 2 < ncols ? ck.z - 512 * V[c4 * 4 + 2] : I32_MAX;
+                            V[c4 * 4 + 3] = I32_MAX;
+                        } else {
+                            V[c4 * 4 + 0] = V[c4 * 4 + 1] = V[c4 * 4 + 2] = V[c4 * 4 + 3] = I32_MAX;
+                        }
                     }
                 }
                 const int h1 = min32(V);
