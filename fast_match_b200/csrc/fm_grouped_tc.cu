@@ -104,24 +104,31 @@ __device__ __forceinline__ unsigned umin32(const int (&v)[32], int base) {
     return umin3i(umin3i(a, b, c), t[9], t[10]);
 }
 
-// gather + norms: packed query rows (only when q_gather is given) and squared norms
-__global__ void k_pack_norms(const uint8_t *__restrict__ pool, const int32_t *__restrict__ gather,
-                             int64_t n, uint8_t *__restrict__ packed, int *__restrict__ norms) {
+// gather + norms in one launch over both pools: rows [0, nq) are query rows (gathered and packed when
+// q_gather is given), rows [nq, nq + nt) target rows.  Also resets the main kernel's group counter.
+__global__ void k_pack_norms(const uint8_t *__restrict__ qpool, const int32_t *__restrict__ gather, int64_t nq,
+                             uint8_t *__restrict__ qpacked, int *__restrict__ qnorms,
+                             const uint8_t *__restrict__ tpool, int64_t nt, int *__restrict__ tnorms,
+                             int *__restrict__ counter) {
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t row = gt >> 3;
+    if (gt == 0) *counter = 0;
+    int64_t row = gt >> 3;
     const int sub = (int)(gt & 7);
+    const bool is_q = row < nq;
+    if (!is_q) row -= nq;
+    const bool live = is_q || row < nt;
     unsigned s = 0;
-    if (row < n) {
-        const int64_t src = gather ? (int64_t)gather[row] : row;
-        const uint4 x = *(const uint4 *)(pool + src * FM_DIM + sub * 16);
-        if (packed) *(uint4 *)(packed + row * FM_DIM + sub * 16) = x;
+    if (live) {
+        const int64_t src = (is_q && gather) ? (int64_t)gather[row] : row;
+        const uint4 x = *(const uint4 *)((is_q ? qpool : tpool) + src * FM_DIM + sub * 16);
+        if (is_q && qpacked) *(uint4 *)(qpacked + row * FM_DIM + sub * 16) = x;
         s = __dp4a(x.x, x.x, s); s = __dp4a(x.y, x.y, s);
         s = __dp4a(x.z, x.z, s); s = __dp4a(x.w, x.w, s);
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (sub == 0 && row < n) norms[row] = (int)s;
+    if (sub == 0 && live) (is_q ? qnorms : tnorms)[row] = (int)s;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -450,11 +457,23 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 }
 
 // crossCheck predicate per local query (needs both passes of the whole grid)
+// Per group: the rows of a group with an empty side (no unit ever touches them) get "no neighbour";
+// the others get their crossCheck flag.
 __global__ void k_mutual(const int64_t *__restrict__ q_off, const int64_t *__restrict__ t_off,
-                         const int32_t *__restrict__ q2t_idx, const int32_t *__restrict__ t2q_idx,
-                         uint8_t *__restrict__ mutual) {
+                         uint32_t *__restrict__ q2t_d2, int32_t *__restrict__ q2t_idx,
+                         int32_t *__restrict__ t2q_idx, uint8_t *__restrict__ mutual) {
     const int g = blockIdx.x;
-    const int64_t q0 = q_off[g], nq = q_off[g + 1] - q0, t0 = t_off[g];
+    const int64_t q0 = q_off[g], nq = q_off[g + 1] - q0, t0 = t_off[g], nt = t_off[g + 1] - t0;
+    if (nq == 0 || nt == 0) {
+        for (int64_t i = threadIdx.x; i < nq; i += blockDim.x) {
+            *(uint2 *)(q2t_d2 + (q0 + i) * 2) = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+            *(int2 *)(q2t_idx + (q0 + i) * 2) = make_int2(-1, -1);
+            if (mutual) mutual[q0 + i] = 0;
+        }
+        for (int64_t j = threadIdx.x; j < nt; j += blockDim.x) t2q_idx[t0 + j] = -1;
+        return;
+    }
+    if (mutual == nullptr) return;
     for (int64_t i = threadIdx.x; i < nq; i += blockDim.x) {
         const int32_t j = q2t_idx[(q0 + i) * 2];
         mutual[q0 + i] = (j >= 0 && t2q_idx[t0 + j] == (int32_t)i) ? 1 : 0;
@@ -490,23 +509,25 @@ int launch_grouped_tc(const uint8_t *qpool, const int32_t *q_gather, const int64
         set_error("grouped tcgen05 path: workspace too small");
         return FM_ENOSPACE;
     }
-    // every slot starts as "no neighbour"; units only exist for groups with both sides non-empty
-    if (total_q > 0) {
-        FM_CUDA_TRY(cudaMemsetAsync(q2t_d2, 0xFF, (size_t)total_q * 8, s));
-        FM_CUDA_TRY(cudaMemsetAsync(q2t_idx, 0xFF, (size_t)total_q * 8, s));
+    if (!(total_q > 0 && total_t > 0 && tpool_rows > 0)) {     // nothing to match: every slot is "no neighbour"
+        if (total_q > 0) {
+            FM_CUDA_TRY(cudaMemsetAsync(q2t_d2, 0xFF, (size_t)total_q * 8, s));
+            FM_CUDA_TRY(cudaMemsetAsync(q2t_idx, 0xFF, (size_t)total_q * 8, s));
+            if (mutual) FM_CUDA_TRY(cudaMemsetAsync(mutual, 0, (size_t)total_q, s));
+        }
+        if (total_t > 0) FM_CUDA_TRY(cudaMemsetAsync(t2q_idx, 0xFF, (size_t)total_t * 4, s));
+        return FM_OK;
     }
-    if (total_t > 0) FM_CUDA_TRY(cudaMemsetAsync(t2q_idx, 0xFF, (size_t)total_t * 4, s));
-    if (total_q > 0 && total_t > 0 && tpool_rows > 0) {
+    {
         uint8_t *w = (uint8_t *)ws;
         int *counter = (int *)w; w += up256(256);
         int *qnorm = (int *)w; w += up256((size_t)(total_q + 8) * 4);
         int *tnorm = (int *)w; w += up256((size_t)(tpool_rows + 8) * 4);
         uint8_t *qpack = q_gather ? w : nullptr;
-        FM_CUDA_TRY(cudaMemsetAsync(counter, 0, 4, s));
-        k_pack_norms<<<(unsigned)((total_q * 8 + 255) / 256), 256, 0, s>>>(qpool, q_gather, total_q, qpack, qnorm);
-        k_pack_norms<<<(unsigned)((tpool_rows * 8 + 255) / 256), 256, 0, s>>>(tpool, nullptr, tpool_rows, nullptr, tnorm);
+        k_pack_norms<<<(unsigned)(((total_q + tpool_rows) * 8 + 255) / 256), 256, 0, s>>>(
+            qpool, q_gather, total_q, qpack, qnorm, tpool, tpool_rows, tnorm, counter);
         FM_CUDA_TRY(cudaGetLastError());
-        count_launch(2);
+        count_launch();
         CUtensorMap map_q, map_t;
         int rc;
         if ((rc = make_map(&map_q, qpack ? qpack : qpool, total_q, FM_DIM, BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
@@ -527,11 +548,10 @@ int launch_grouped_tc(const uint8_t *qpool, const int32_t *q_gather, const int64
         FM_CUDA_TRY(cudaGetLastError());
         count_launch();
     }
-    if (mutual && total_q > 0) {
-        k_mutual<<<G, 128, 0, s>>>(q_off, t_off, q2t_idx, t2q_idx, mutual);
-        FM_CUDA_TRY(cudaGetLastError());
-        count_launch();
-    }
+    // rows of groups with an empty side + (optionally) the crossCheck flags
+    k_mutual<<<G, 128, 0, s>>>(q_off, t_off, q2t_d2, q2t_idx, t2q_idx, mutual);
+    FM_CUDA_TRY(cudaGetLastError());
+    count_launch();
     return FM_OK;
 }
 
