@@ -64,6 +64,8 @@ def test_sass_has_blackwell_tensor_and_tma_instructions():
         pytest.skip("cuobjdump not available")
     build.build()
     sass = subprocess.run([cuobjdump, "-sass", build.LIB], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCIMMA", "LDTM", "UTMALDG"):
+    # tcgen05.mma kind::i8, TMEM loads, TMA loads; and the CTA-pair forms of the dense kernel:
+    # cta_group::2 MMA, 2-CTA TMA load, multicast commit
+    for mnemonic in ("UTCIMMA", "LDTM", "UTMALDG", "UTCIMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", build.LIB], capture_output=True, text=True).stdout
