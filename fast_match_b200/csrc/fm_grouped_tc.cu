@@ -112,23 +112,36 @@ __global__ void k_pack_norms(const uint8_t *__restrict__ qpool, const int32_t *_
                              int *__restrict__ counter) {
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (gt == 0) *counter = 0;
-    int64_t row = gt >> 3;
-    const int sub = (int)(gt & 7);
-    const bool is_q = row < nq;
-    if (!is_q) row -= nq;
-    const bool live = is_q || row < nt;
-    unsigned s = 0;
-    if (live) {
-        const int64_t src = (is_q && gather) ? (int64_t)gather[row] : row;
-        const uint4 x = *(const uint4 *)((is_q ? qpool : tpool) + src * FM_DIM + sub * 16);
-        if (is_q && qpacked) *(uint4 *)(qpacked + row * FM_DIM + sub * 16) = x;
-        s = __dp4a(x.x, x.x, s); s = __dp4a(x.y, x.y, s);
-        s = __dp4a(x.z, x.z, s); s = __dp4a(x.w, x.w, s);
+    const int sub = (int)(gt & 7);                // 8 threads (16 B each) per descriptor
+    constexpr int U = 4;                          // descriptors per thread group: 4 loads in flight per thread
+    const int64_t half = (nq + nt + U - 1) / U;   // row r of this group and r + half, r + 2 half, ...
+    uint4 x[U];
+    int64_t row[U];
+    bool is_q[U], live[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+        int64_t r = (gt >> 3) + k * half;
+        live[k] = (gt >> 3) < half && r < nq + nt;
+        is_q[k] = r < nq;
+        if (!is_q[k]) r -= nq;
+        row[k] = r;
+        x[k] = make_uint4(0, 0, 0, 0);
+        if (live[k]) {
+            const int64_t src = (is_q[k] && gather) ? (int64_t)gather[r] : r;
+            x[k] = *(const uint4 *)((is_q[k] ? qpool : tpool) + src * FM_DIM + sub * 16);
+        }
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (sub == 0 && live) (is_q ? qnorms : tnorms)[row] = (int)s;
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+        if (live[k] && is_q[k] && qpacked) *(uint4 *)(qpacked + row[k] * FM_DIM + sub * 16) = x[k];
+        unsigned s = 0;
+        s = __dp4a(x[k].x, x[k].x, s); s = __dp4a(x[k].y, x[k].y, s);
+        s = __dp4a(x[k].z, x[k].z, s); s = __dp4a(x[k].w, x[k].w, s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (sub == 0 && live[k]) (is_q[k] ? qnorms : tnorms)[row[k]] = (int)s;
+    }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -524,7 +537,7 @@ int launch_grouped_tc(const uint8_t *qpool, const int32_t *q_gather, const int64
         int *qnorm = (int *)w; w += up256((size_t)(total_q + 8) * 4);
         int *tnorm = (int *)w; w += up256((size_t)(tpool_rows + 8) * 4);
         uint8_t *qpack = q_gather ? w : nullptr;
-        k_pack_norms<<<(unsigned)(((total_q + tpool_rows) * 8 + 255) / 256), 256, 0, s>>>(
+        k_pack_norms<<<(unsigned)((((total_q + tpool_rows + 3) / 4) * 8 + 255) / 256), 256, 0, s>>>(
             qpool, q_gather, total_q, qpack, qnorm, tpool, tpool_rows, tnorm, counter);
         FM_CUDA_TRY(cudaGetLastError());
         count_launch();
