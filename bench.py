@@ -9,8 +9,13 @@ Workload (BASELINE.json configs[2], "c3"): synthetic 10-MP pair, 50 000 x 50 000
 pair.  With N GPUs every rank matches its own pair (independent image pairs: no data-path
 collective, weak scaling); `value` = query descriptors matched per second over all ranks.
 Extra legs on the same JSON line: "grouped" (configs[3], 10k Fast-Match cell rounds in one
-launch, HBM roofline) and "sharded" (configs[4], 1M x 1M with the target set sharded over the
-N ranks + NCCL all-gather + merge; strong scaling).
+launch, HBM roofline on the whole call), "sharded" (configs[4], 1M x 1M with the target set sharded
+over the N ranks + NCCL exchange + merge; strong scaling, with a same-run 1-GPU denominator and an
+oracle-checked sample of rows), "c2" (configs[1], Ratio-Match on the graf pair and 5000 x 5000 through
+the host entry point), "flann_recall" (the reference's approximate FLANN sites scored against the
+exact result) and "fastmatch_readme" (configs[0]).  Every leg that has a CPU counterpart in the
+reference carries its own cpu_baseline (cv2 on the box's host cores, N = 1 only) and every GPU
+result that leaves a leg is checked against oracle/ on a seeded sample outside the timed region.
 """
 import argparse
 import json
@@ -166,7 +171,8 @@ def run_reference(args):
             "config": {"workload": "c3: 50000x50000 u8 128-d, exact top-2 + ratio 0.7; each step = %d-query sample "
                                    "x all 50000 targets on the host CPU (%s)" % (sample, what)},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
-                             "sample": "%d queries x 50000 targets per step" % sample},
+                             "sample": "sampled: %d of the 50000 queries x all 50000 targets per step (brute force is linear in M, "
+                                       "so queries/s carries over to the full pair)" % sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -267,7 +273,7 @@ def run_ours(args):
            torch.empty(M_C3, dtype=torch.uint8, device=dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    def step():   # exact top-2 + Lowe ratio test, fused (fm_ratio_match_u8)
+    def step():   # exact top-2 + Lowe ratio test, fused (fm_ratio_match_u8); no torch kernel involved
         return backend.ratio_match(q_dev, t_dev, TAU, out=out)[3]
 
     for _ in range(args.warmup):
@@ -326,7 +332,7 @@ def run_ours(args):
     except Exception:
         pass
     bf16 = peaks.get("bf16_tflops")
-    peak_tops = 2.0 * bf16 if bf16 else 2.0 * 1590.0
+    proxy_tops = 2.0 * bf16 if bf16 else 2.0 * 1590.0
     ops = 2.0 * M_C3 * N_C3 * 128
     traffic = {}
     try:
@@ -335,15 +341,17 @@ def run_ours(args):
         pass
     k_ms = kern_ms / max(kern_n, 1)
     achieved = ops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "k_top2_tc_pair", "achieved": achieved, "peak": peak_tops, "unit": "TOP/s",
-                "frac": achieved / peak_tops,
+    roofline = {"bound": "tensor", "kernel": "k_top2_tc_pair", "achieved": achieved, "peak": 4500.0, "unit": "TOP/s",
+                "frac": achieved / 4500.0,
+                "peak_source": "B200 dense int8 datasheet peak (4.5 POP/s), the denominator BASELINE.json's north_star "
+                               "names; MEASURED_PEAKS.json has no int8 entry, so the measured proxies are listed beside it",
+                "frac_of_datasheet_4500": achieved / 4500.0,
+                "frac_of_2x_measured_bf16": achieved / proxy_tops, "proxy_2x_measured_bf16_tops": proxy_tops,
                 "traffic": (traffic.get("k_top2_tc_c3_50k") or {}).get("bytes"),
                 "traffic_note": "DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json); "
                                 "the kernel is tensor-bound, its algorithmic HBM bytes are (M+N)*128 + 16*M = 13.6 MB",
-                "peak_source": ("2 x bf16_tflops of MEASURED_PEAKS.json (u8 tensor rate is twice bf16; the file has no "
-                                "int8 entry)" if bf16 else "2 x 1.59 PFLOP/s fallback"),
-                "frac_of_datasheet_4500": achieved / 4500.0, "kernel_ms": k_ms, "kernel_launches_timed": kern_n,
-                "algorithmic_ops_per_launch": ops}
+                "kernel_ms": k_ms, "kernel_launches_timed": kern_n, "algorithmic_ops_per_launch": ops,
+                "step_frac_of_datasheet_4500": ops / (total_ms / args.steps * 1e-3) / 1e12 / 4500.0}
     try:   # same-run measured int8 GEMM throughput, for context
         a8 = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device=dev)
         b8 = torch.randint(-8, 8, (8192, 8192), dtype=torch.int8, device=dev).t()
@@ -355,6 +363,7 @@ def run_ours(args):
             s.record(); torch._int_mm(a8, b8); e.record(); torch.cuda.synchronize()
             best = min(best, s.elapsed_time(e))
         roofline["int8_gemm_8192_tops_same_run"] = 2.0 * 8192 ** 3 / (best * 1e-3) / 1e12
+        roofline["frac_of_int8_gemm_same_run"] = achieved / roofline["int8_gemm_8192_tops_same_run"]
         del a8, b8
     except Exception as ex:  # noqa: BLE001
         roofline["int8_gemm_8192_tops_same_run"] = None
@@ -374,18 +383,21 @@ def run_ours(args):
     # ---------------- extra leg: grouped launch (configs[3]) ----------------
     if not args.no_extra:
         try:
-            line["grouped"] = grouped_leg(args, dev, peaks, backend)
+            line["grouped"] = grouped_leg(args, dev, peaks, backend, rank == 0 and world == 1 and not args.no_cpu)
         except Exception as ex:  # noqa: BLE001
             line["grouped"] = {"error": repr(ex)}
         try:
-            line["sharded"] = sharded_leg(args, dev, world, rank, backend, sharded, barrier, max_over_ranks)
+            line["sharded"] = sharded_leg(args, dev, world, rank, backend, sharded, barrier, max_over_ranks,
+                                          rank == 0 and world == 1 and not args.no_cpu)
         except Exception as ex:  # noqa: BLE001
             line["sharded"] = {"error": repr(ex)}
         if rank == 0 and world == 1:
-            try:
-                line["fastmatch_readme"] = fastmatch_leg(dev)
-            except Exception as ex:  # noqa: BLE001
-                line["fastmatch_readme"] = {"error": repr(ex)}
+            for key, leg in (("fastmatch_readme", lambda: fastmatch_leg(dev)), ("c2", lambda: c2_leg(dev, backend)),
+                             ("flann_recall", lambda: flann_leg(dev, backend))):
+                try:
+                    line[key] = leg()
+                except Exception as ex:  # noqa: BLE001
+                    line[key] = {"error": repr(ex)}
 
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline()
@@ -402,7 +414,8 @@ def _traffic(key):
         return None
 
 
-def grouped_leg(args, dev, peaks, backend):
+def grouped_leg(args, dev, peaks, backend, with_cpu):
+    import numpy as np
     import torch
     G = args.groups
     g = torch.Generator(device="cpu"); g.manual_seed(1238)
@@ -426,7 +439,7 @@ def grouped_leg(args, dev, peaks, backend):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     fn = lambda: backend.grouped_mutual(qpool, qo, tpool, to, max_nq=int(nq.max()), total_q=Q, total_t=T)
     for _ in range(3):
-        fn()
+        res = fn()
     torch.cuda.synchronize()
     backend.profile_enable(True); backend.profile_read(reset=True)
     ts = []
@@ -441,14 +454,64 @@ def grouped_leg(args, dev, peaks, backend):
     byts = 128.0 * (Q + T) + 16.0 * Q + 4.0 * T + 16.0 * (G + 1)
     hbm = peaks.get("hbm_gbs", 6650.0)
     kms1 = kms / max(kn, 1)
-    return {"workload": "c4: %d groups, n_q,n_t ~ U[32,512], packed, one grouped launch" % G, "ms": ms,
-            "groups_per_s": G / (ms * 1e-3), "query_descriptors_per_s": Q / (ms * 1e-3),
-            "total_q": Q, "total_t": T, "mutual_matches": None,
-            "roofline": {"bound": "hbm", "kernel": "k_grouped_tc", "achieved": byts / (kms1 * 1e-3) / 1e9 if kms1 else None, "peak": hbm,
-                         "unit": "GB/s", "frac": (byts / (kms1 * 1e-3) / 1e9 / hbm) if kms1 else None,
-                         "traffic": _traffic("k_grouped_tc_c4"),
-                         "algorithmic_bytes": byts, "kernel_ms": kms1,
-                         "tensor_ops": float((2 * 128 * nq.double() * nt.double()).sum())}}
+    out = {"workload": "c4: %d groups, n_q,n_t ~ U[32,512], packed, one grouped launch" % G, "ms": ms,
+           "groups_per_s": G / (ms * 1e-3), "query_descriptors_per_s": Q / (ms * 1e-3),
+           "total_q": Q, "total_t": T, "mutual_matches": int(res[3].sum().item()),
+           # the roofline is quoted on the CALL (norm pass + grouped kernel + crossCheck flags), not on its main kernel
+           "roofline": {"bound": "hbm", "scope": "whole fm_grouped_mutual_u8 call", "achieved": byts / (ms * 1e-3) / 1e9,
+                        "peak": hbm, "unit": "GB/s", "frac": byts / (ms * 1e-3) / 1e9 / hbm,
+                        "peak_source": "hbm_gbs of MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "6.65 TB/s fallback",
+                        "traffic": _traffic("grouped_call_c4"), "algorithmic_bytes": byts,
+                        "main_kernel": "k_grouped_tc", "main_kernel_ms": kms1,
+                        "main_kernel_frac": (byts / (kms1 * 1e-3) / 1e9 / hbm) if kms1 else None,
+                        "main_kernel_traffic": _traffic("k_grouped_tc_c4"),
+                        "tensor_ops": float((2 * 128 * nq.double() * nt.double()).sum())}}
+    # ---- oracle check of a seeded sample of groups (outside the timed region)
+    try:
+        import oracle
+        rs = np.random.default_rng(1238)
+        pickg = np.sort(rs.choice(G, min(200, G), replace=False))
+        qo_h, to_h = q_off.numpy(), t_off.numpy()
+        d2_h, idx_h, t2q_h = res[0].cpu().numpy().view(np.uint32), res[1].cpu().numpy(), res[2].cpu().numpy()
+        qrows = np.concatenate([np.arange(qo_h[i], qo_h[i + 1]) for i in pickg])
+        trows = np.concatenate([np.arange(to_h[i], to_h[i + 1]) for i in pickg])
+        sq_off = np.concatenate([[0], np.cumsum([qo_h[i + 1] - qo_h[i] for i in pickg])]).astype(np.int64)
+        st_off = np.concatenate([[0], np.cumsum([to_h[i + 1] - to_h[i] for i in pickg])]).astype(np.int64)
+        qs = qpool[torch.from_numpy(qrows).to(dev)].cpu().numpy()
+        tsub = tpool[torch.from_numpy(trows).to(dev)].cpu().numpy()
+        od2, oidx, ot2q = oracle.c_grouped_mutual(qs, sq_off, tsub, st_off)
+        out["parity_sample_ok"] = bool(np.array_equal(d2_h[qrows], od2) and np.array_equal(idx_h[qrows], oidx)
+                                       and np.array_equal(t2q_h[trows], ot2q))
+        out["parity_sample"] = "%d seeded groups (%d queries, %d targets) vs oracle.c_grouped_mutual: top-2 d2 + idx per query, top-1 idx per target" % (len(pickg), len(qrows), len(trows))
+    except Exception as ex:  # noqa: BLE001
+        out["parity_sample_ok"] = None
+        out["parity_sample_error"] = repr(ex)
+    # ---- the reference's CPU path for the same rounds: one BFMatcher(crossCheck=True).knnMatch(k=1) per
+    #      group on float32 descriptors (fastmatch.pyx:161-162), on a seeded 1000-group subset
+    if with_cpu:
+        try:
+            import cv2
+            cv2.setNumThreads(os.cpu_count() or 1)
+            rs = np.random.default_rng(1238)
+            sub = np.sort(rs.choice(G, min(1000, G), replace=False))
+            qo_h, to_h = q_off.numpy(), t_off.numpy()
+            qs = [qpool[qo_h[i]:qo_h[i + 1]].cpu().numpy().astype(np.float32) for i in sub]
+            tsl = [tpool[to_h[i]:to_h[i + 1]].cpu().numpy().astype(np.float32) for i in sub]
+            cv2.BFMatcher(cv2.NORM_L2, crossCheck=True).knnMatch(qs[0], tsl[0], k=1)
+            t0 = time.perf_counter()
+            n_pairs = 0
+            for a, b in zip(qs, tsl):
+                n_pairs += sum(1 for m in cv2.BFMatcher(cv2.NORM_L2, crossCheck=True).knnMatch(a, b, k=1) if m)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": len(sub) / dt, "unit": "groups/s", "cores": cv2.getNumThreads(), "kind": "reference",
+                                   "ms_for_all_groups_extrapolated": 1e3 * dt * G / len(sub),
+                                   "sample": "%d seeded groups of the %d, one cv2.BFMatcher(NORM_L2, crossCheck=True).knnMatch(k=1) per "
+                                             "group on float32 (fastmatch.pyx:161-162), %.2f s; x%.0f extrapolated to all groups"
+                                             % (len(sub), G, dt, G / len(sub))}
+            out["speedup_vs_cpu_extrapolated"] = (1e3 * dt * G / len(sub)) / ms
+        except Exception as ex:  # noqa: BLE001
+            out["cpu_baseline"] = {"error": repr(ex)}
+    return out
 
 
 def fastmatch_leg(dev):
@@ -505,8 +568,10 @@ def _graf1_features(gold):
     return g["graf1_desc"], g["graf1_pos"]
 
 
-def sharded_leg(args, dev, world, rank, backend, sharded, barrier, max_over_ranks):
+def sharded_leg(args, dev, world, rank, backend, sharded, barrier, max_over_ranks, with_cpu):
+    import numpy as np
     import torch
+    import torch.distributed as dist
     Ntot = Mtot = args.sharded_n
     lo, hi = sharded.shard_range(Ntot, rank, world)
     q = siftlike_torch(0, Mtot, 21, dev)
@@ -514,23 +579,178 @@ def sharded_leg(args, dev, world, rank, backend, sharded, barrier, max_over_rank
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step():
-        _, d2, idx = sharded.sharded_top2(q, t, lo)
-        _, mask = backend.ratio(d2[:, 0], den_d2=d2[:, 1], tau=TAU, want_ratio=False)
-        return mask
+        return sharded.ratio_match_sharded(q, t, lo, TAU, want_ratio=False)
     step(); barrier()
     ts = []
     for _ in range(3):
         flush.zero_()
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); mask = step(); b.record()
+        a.record(); idx, d2, _, mask = step(); b.record()
         barrier()
         ts.append(max_over_ranks(a.elapsed_time(b)))
     ms = sorted(ts)[len(ts) // 2]
     ops = 2.0 * Mtot * Ntot * 128
-    return {"workload": "c5: %dx%d, target set sharded over %d GPU(s), all-gather of packed top-2 keys + merge" % (Mtot, Ntot, world),
-            "ms": ms, "value": Mtot / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
-            "tops_aggregate": ops / (ms * 1e-3) / 1e12, "matched_queries": int(mask.sum().item())}
+    matched = sharded.count_true(mask)
+    out = {"workload": "c5: %dx%d, target set sharded over %d GPU(s), exchange of packed top-2 keys + merge + ratio test" % (Mtot, Ntot, world),
+           "ms": ms, "value": Mtot / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
+           "tops_aggregate": ops / (ms * 1e-3) / 1e12, "matched_queries": matched,
+           "exchange": sharded.exchange_description(world)}
+    # ---- oracle check over the exchange (outside the timed region): 256 fixed query rows against this
+    #      rank's shard on the host, packed keys gathered across ranks, oracle merge, compared with the GPU rows
+    try:
+        import oracle
+        rows = torch.linspace(0, Mtot - 1, 256).long()
+        okeys = oracle.pack_keys(*oracle.c_top2(q[rows.to(dev)].cpu().numpy(), t.cpu().numpy(), t_index_base=lo))
+        if world > 1:
+            mine = torch.from_numpy(okeys.view(np.int64)).to(dev)
+            allk = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allk.view(world * mine.shape[0], 2), mine)
+            okeys_all = allk.cpu().numpy().view(np.uint64)
+        else:
+            okeys_all = okeys[None]
+        merged = oracle.c_merge_top2(okeys_all)
+        full_idx, full_d2 = sharded.rows_of(idx, rows, dev), sharded.rows_of(d2, rows, dev)
+        got = oracle.pack_keys(full_d2.cpu().numpy().view(np.uint32), full_idx.cpu().numpy())
+        ok = bool(np.array_equal(got, merged))
+        if world > 1:
+            flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item() > 0.5)
+        out["parity_sample_ok"] = ok
+        out["parity_sample"] = "256 evenly spaced query rows vs oracle.c_top2 on every rank's shard + oracle.c_merge_top2"
+        out["idx_xor_checksum"] = sharded.xor_checksum(idx)
+    except Exception as ex:  # noqa: BLE001
+        out["parity_sample_ok"] = None
+        out["parity_sample_error"] = repr(ex)
+    # ---- same-run, same-box denominator of the strong-scaling curve: rank 0 alone, unsharded
+    if world > 1:
+        ms1 = 0.0
+        if rank == 0:
+            del t
+            t_full = plant_torch(q, siftlike_torch(0, Ntot, 22, dev), 0, 23)
+            solo = lambda: backend.ratio_match(q, t_full, TAU)
+            solo(); torch.cuda.synchronize()
+            t1 = []
+            for _ in range(3):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); r = solo(); b.record(); torch.cuda.synchronize()
+                t1.append(a.elapsed_time(b))
+            ms1 = sorted(t1)[1]
+            out["matched_queries_1gpu_same_run"] = int(r[3].sum().item())
+            out["idx_xor_checksum_1gpu_same_run"] = sharded.xor_checksum(r[1], distributed=False)
+            del t_full
+        barrier()
+        ms1 = max_over_ranks(ms1)
+        out["ms_1gpu_same_run"] = ms1
+        out["efficiency"] = ms1 / (world * ms)
+        out["speedup_vs_1gpu_same_run"] = ms1 / ms
+    # ---- the reference's CPU matcher on this shape: cv2.BFMatcher refuses >= 2^18 train rows, so the targets
+    #      go in <= 262143-row chunks with a host merge; 4096 sampled queries, extrapolated linearly in M
+    if with_cpu:
+        try:
+            import cv2
+            import oracle
+            cv2.setNumThreads(os.cpu_count() or 1)
+            sample = 4096
+            rows = torch.linspace(0, Mtot - 1, sample).long().to(dev)
+            qf = q[rows].cpu().numpy().astype(np.float32)
+            tf = t.cpu().numpy().astype(np.float32)
+            t0 = time.perf_counter()
+            bf = cv2.BFMatcher(cv2.NORM_L2, crossCheck=False)
+            parts = [bf.knnMatch(qf, tf[c:c + 262143], k=2) for c in range(0, len(tf), 262143)]
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": sample / dt, "unit": UNIT, "cores": cv2.getNumThreads(), "kind": "reference",
+                                   "s_for_all_queries_extrapolated": dt * Mtot / sample,
+                                   "sample": "%d evenly spaced queries x all %d targets in %d chunks of <= 262143 rows, cv2.BFMatcher(NORM_L2)"
+                                             ".knnMatch(k=2) on float32 (matcher only; the host merge of the chunks is not timed), %.1f s; "
+                                             "extrapolated linearly in M" % (sample, Ntot, len(parts), dt)}
+            out["speedup_vs_cpu_extrapolated"] = (dt * Mtot / sample) / (ms * 1e-3)
+        except Exception as ex:  # noqa: BLE001
+            out["cpu_baseline"] = {"error": repr(ex)}
+    return out
+
+
+def c2_leg(dev, backend):
+    """configs[1]: Ratio-Match (Classic Matching.ipynb cell 3) on the full graf pair (frozen SIFT descriptors,
+    3668 x 2674) and on a synthetic 5000 x 5000 pair, through the host entry point (numpy in, numpy out,
+    copies inside the timed region), next to cv2.BFMatcher.knnMatch(k=2) + the ratio on the host cores."""
+    import cv2
+    import numpy as np
+    import oracle
+    from fast_match_b200 import synth
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bf_golden.npz"))
+    cases = [("graf4_vs_graf1", g["graf4_desc"], g["graf1_desc"]), ("synthetic_5000", ) + synth.make_pair(5000, 5000, seed=1236)]
+    cv2.setNumThreads(os.cpu_count() or 1)
+    out = {"workload": "c2: Ratio-Match exact top-2 + ratio 0.7, host buffers through fm_top2_host_u8 (wall time incl. H2D/D2H)"}
+    for name, q, t in cases:
+        q, t = np.ascontiguousarray(q, np.uint8), np.ascontiguousarray(t, np.uint8)
+        for _ in range(3):
+            d2, idx, _, mask = backend.top2_host(q, t, device=dev.index, want_dist=False, tau=TAU)
+        ts = []
+        for _ in range(10):
+            t0 = time.perf_counter()
+            d2, idx, _, mask = backend.top2_host(q, t, device=dev.index, want_dist=False, tau=TAU)
+            ts.append(time.perf_counter() - t0)
+        ours = sorted(ts)[len(ts) // 2]
+        qf, tf = q.astype(np.float32), t.astype(np.float32)
+        cs = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            mm = cv2.BFMatcher(cv2.NORM_L2, crossCheck=False).knnMatch(qf, tf, k=2)
+            cs.append(time.perf_counter() - t0)
+        cpu = sorted(cs)[1]
+        cidx = np.array([[m[0].trainIdx, m[1].trainIdx] for m in mm], np.int32)
+        cdist = np.array([[m[0].distance, m[1].distance] for m in mm], np.float32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            cmask = (cdist[:, 0].astype(np.float64) / cdist[:, 1].astype(np.float64)) < TAU
+        od2, oidx = oracle.c_top2(q, t)
+        out[name] = {"M": len(q), "N": len(t), "ms": 1e3 * ours, "query_descriptors_per_s": len(q) / ours,
+                     "matched_queries": int(mask.sum()),
+                     "identical_to_cv2": bool(np.array_equal(idx, cidx) and np.array_equal(np.sqrt(d2.astype(np.float32)), cdist)
+                                              and np.array_equal(mask.astype(bool), cmask)),
+                     "identical_to_oracle": bool(np.array_equal(d2, od2) and np.array_equal(idx, oidx)),
+                     "cpu_baseline": {"ms": 1e3 * cpu, "value": len(q) / cpu, "unit": UNIT, "cores": cv2.getNumThreads(), "kind": "reference",
+                                      "sample": "the full pair, cv2.BFMatcher(NORM_L2).knnMatch(k=2) on float32, matcher only"},
+                     "speedup_vs_cpu": cpu / ours}
+    return out
+
+
+def flann_leg(dev, backend):
+    """The reference's approximate sites (matchutil.flann_match matchutil.py:46-67: algorithm 1, trees 5, checks 200;
+    match_flann Classic Matching.ipynb cell 4: trees 8, checks 400) cannot be matched bit for bit -- FLANN's
+    kd-forest is randomised.  Report its recall against the exact CUDA result on the same descriptors."""
+    import cv2
+    import numpy as np
+    import torch
+    g = np.load(os.path.join(ROOT, "tests", "golden", "bf_golden.npz"))
+    g4, g1 = np.ascontiguousarray(g["graf4_desc"], np.uint8), np.ascontiguousarray(g["graf1_desc"], np.uint8)
+    out = {"what": "cv2.FlannBasedMatcher.knnMatch(k=2) vs the exact top-2 of fm_top2_u8 on the frozen graf descriptors: "
+                   "recall@1 = share of queries whose FLANN nearest index is the exact nearest, recall@2 = both slots equal, "
+                   "dist_inflation = mean FLANN distance / exact distance per slot"}
+    for cname, q, t in (("graf4_self", g4, g4), ("graf4_vs_graf1", g4, g1)):
+        d2, idx = backend.top2(torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev))
+        eidx = idx.cpu().numpy()
+        edist = np.sqrt(d2.cpu().numpy().view(np.uint32).astype(np.float32))
+        qf, tf = q.astype(np.float32), t.astype(np.float32)
+        for pname, trees, checks in (("matchutil_trees5_checks200", 5, 200), ("notebook_trees8_checks400", 8, 400)):
+            t0 = time.perf_counter()
+            fl = cv2.FlannBasedMatcher(dict(algorithm=1, trees=trees), dict(checks=checks))
+            mm = fl.knnMatch(qf, tf, k=2)
+            dt = time.perf_counter() - t0
+            fidx = np.array([[m[0].trainIdx, m[1].trainIdx] for m in mm], np.int32)
+            fdist = np.array([[m[0].distance, m[1].distance] for m in mm], np.float32)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                infl = [float(np.mean((fdist[:, k] / edist[:, k])[edist[:, k] > 0])) for k in (0, 1)]
+                fr = fdist[:, 0].astype(np.float64) / fdist[:, 1].astype(np.float64)
+                er = edist[:, 0].astype(np.float64) / edist[:, 1].astype(np.float64)
+            out["%s/%s" % (cname, pname)] = {
+                "recall_at_1": float(np.mean(fidx[:, 0] == eidx[:, 0])), "recall_at_2": float(np.mean(np.all(fidx == eidx, axis=1))),
+                "dist_inflation_slot0": infl[0], "dist_inflation_slot1": infl[1],
+                "ratio_test_0.7_flann": int(np.sum(fr < TAU)), "ratio_test_0.7_exact": int(np.sum(er < TAU)),
+                "flann_ms": 1e3 * dt}
+    return out
 
 
 def main():

@@ -137,7 +137,7 @@ def ratio_match(q, t, tau, algo=FM_ALGO_AUTO, want_ratio=False, out=None):
         _check(L.fm_ratio_match_u8(_ptr(q), M, _ptr(t), N, float(tau), _ptr(d2), _ptr(idx), _ptr(r),
                                    _ptr(mask), _ptr(ws), ws.numel(), int(algo), _stream(dev)),
                "fm_ratio_match_u8")
-    return d2, idx, r, mask.bool()
+    return d2, idx, r, mask.view(torch.bool)     # 0/1 bytes: a view, no kernel
 
 
 def ratio(num_d2, den_d2=None, den_f32=None, tau=0.7, want_ratio=True):
@@ -157,7 +157,7 @@ def ratio(num_d2, den_d2=None, den_f32=None, tau=0.7, want_ratio=True):
         _check(lib().fm_ratio_f32sqrt(_ptr(num_d2), num_d2.stride(0) if M else 1, den_ptr,
                                       den_stride, _ptr(den_f32), M, float(tau), _ptr(r), _ptr(m),
                                       _stream(dev)), "fm_ratio_f32sqrt")
-    return r, m.bool()
+    return r, m.view(torch.bool)
 
 
 def grouped_mutual(qpool, q_off, tpool, t_off, q_gather=None, t_base=None, max_nq=None, total_q=None,
@@ -191,7 +191,7 @@ def grouped_mutual(qpool, q_off, tpool, t_off, q_gather=None, t_base=None, max_n
                                       _ptr(t_off), _ptr(t_base), G, total_q, total_t, tpool_rows, int(max_nq), _ptr(d2),
                                       _ptr(idx), _ptr(t2q), _ptr(mutual), _ptr(ws), ws.numel(), int(algo),
                                       _stream(dev)), "fm_grouped_mutual_u8")
-    return d2, idx, t2q, (mutual.bool() if want_mutual else None)
+    return d2, idx, t2q, (mutual.view(torch.bool) if want_mutual else None)
 
 
 def merge_top2(keys, want_unpacked=True):

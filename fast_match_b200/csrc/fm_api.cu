@@ -24,13 +24,18 @@ static std::atomic<long long> g_launches{0};
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<cudaEvent_t> g_prof_events;   // start/stop pairs
-static cudaEvent_t g_prof_open = nullptr;
+// the bracket a launcher has open: begin and end run on the same thread inside one call, so the
+// slot is per thread and concurrent calls on other threads / streams cannot pair up each other's events
+static thread_local cudaEvent_t g_prof_open = nullptr;
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void prof_begin(cudaStream_t s) {
-    std::lock_guard<std::mutex> lock(g_prof_mu);
-    if (!g_prof_on) return;
+    {
+        std::lock_guard<std::mutex> lock(g_prof_mu);
+        if (!g_prof_on) return;
+    }
+    if (g_prof_open) { cudaEventDestroy(g_prof_open); g_prof_open = nullptr; }   // an aborted call
     cudaEvent_t a;
     if (cudaEventCreate(&a) != cudaSuccess) return;
     cudaEventRecord(a, s);
@@ -38,11 +43,11 @@ void prof_begin(cudaStream_t s) {
 }
 
 void prof_end(cudaStream_t s) {
-    std::lock_guard<std::mutex> lock(g_prof_mu);
-    if (!g_prof_on || !g_prof_open) return;
+    if (!g_prof_open) return;
     cudaEvent_t b;
-    if (cudaEventCreate(&b) != cudaSuccess) return;
+    if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(g_prof_open); g_prof_open = nullptr; return; }
     cudaEventRecord(b, s);
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     g_prof_events.push_back(g_prof_open);
     g_prof_events.push_back(b);
     g_prof_open = nullptr;
@@ -313,15 +318,17 @@ int fm_merge_top2(const uint64_t *keys, int32_t S, int64_t M, uint64_t *out_keys
 
 // ---- host-buffer convenience --------------------------------------------------------
 namespace {
-struct HostCtx {
+constexpr int HOST_MAX_DEVICES = 64;
+struct HostCtx {                 // one per device: staging buffers, two streams, events
     std::mutex mu;
-    int device = -1;
-    cudaStream_t stream = nullptr;
+    bool ready = false;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t in_ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
     uint8_t *pin_in = nullptr; size_t pin_in_cap = 0;
     uint8_t *pin_out = nullptr; size_t pin_out_cap = 0;
     uint8_t *dev = nullptr; size_t dev_cap = 0;
 };
-HostCtx g_host;
+HostCtx g_host[HOST_MAX_DEVICES];
 
 int ensure(uint8_t **p, size_t *cap, size_t need, bool pinned) {
     if (*cap >= need) return FM_OK;
@@ -333,13 +340,128 @@ int ensure(uint8_t **p, size_t *cap, size_t need, bool pinned) {
     return FM_OK;
 }
 inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
-}  // namespace
 
-static bool is_device_accessible_host(const void *p) {
+bool is_device_accessible_host(const void *p) {
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return at.type == cudaMemoryTypeHost;
 }
+
+struct DeviceGuard {             // the caller's current device is restored on every exit path
+    int prev = -1;
+    bool switched = false;
+    int enter(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        FM_CUDA_TRY(cudaSetDevice(device));
+        switched = true;
+        return FM_OK;
+    }
+    ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+};
+
+// Body of fm_top2_host_u8 (runs with the context locked and the device selected).
+// The queries go up in two halves on a copy stream while the compute stream already matches the
+// first half against the targets; each half's results go back while the other half computes.
+// Row halves are independent, so nothing has to be merged.
+int top2_host_locked(HostCtx &c, const uint8_t *q_host, int64_t M, const uint8_t *t_host, int64_t N,
+                     uint32_t *d2_host, int32_t *idx_host, float *dist_host, double tau, uint8_t *mask_host,
+                     bool *enqueued) {
+    if (!c.ready) {
+        FM_CUDA_TRY(cudaStreamCreateWithFlags(&c.compute, cudaStreamNonBlocking));
+        FM_CUDA_TRY(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+        for (int h = 0; h < 2; ++h) {
+            FM_CUDA_TRY(cudaEventCreateWithFlags(&c.in_ready[h], cudaEventDisableTiming));
+            FM_CUDA_TRY(cudaEventCreateWithFlags(&c.done[h], cudaEventDisableTiming));
+        }
+        c.ready = true;
+    }
+    // two halves only when the second launch's fixed cost is small next to the copy it hides
+    const int halves = (M >= 16384 && N >= 4096) ? 2 : 1;
+    const int64_t m0 = halves == 2 ? ((M / 2 + 511) / 512) * 512 : M;      // whole M-blocks in the first half
+    const int64_t hm[2] = {m0, M - m0}, hbeg[2] = {0, m0};
+    const size_t qb = (size_t)M * FM_DIM, tb = (size_t)N * FM_DIM;
+    const size_t ob_d2 = (size_t)M * 2 * 4, ob_idx = ob_d2, ob_dist = dist_host ? ob_d2 : 0;
+    const size_t ob_mask = mask_host ? (size_t)M : 0;
+    size_t wsb = up256(fm_top2_workspace_bytes(hm[0], N));
+    if (hm[1] > 0 && up256(fm_top2_workspace_bytes(hm[1], N)) > wsb) wsb = up256(fm_top2_workspace_bytes(hm[1], N));
+    // device layout: q | t | d2 | idx | dist | mask | ws
+    const size_t o_q = 0, o_t = up256(qb), o_d2 = o_t + up256(tb), o_idx = o_d2 + up256(ob_d2),
+                 o_dist = o_idx + up256(ob_idx), o_mask = o_dist + up256(ob_dist),
+                 o_ws = o_mask + up256(ob_mask), total = o_ws + wsb;
+    int rc;
+    if ((rc = ensure(&c.dev, &c.dev_cap, total, false)) != FM_OK) return rc;
+    // inputs: pinned / registered host memory is copied straight from the caller's buffer,
+    // pageable memory goes through the library's pinned staging area (chunk by chunk, so the
+    // staging memcpy of one piece overlaps the DMA of the previous one)
+    const bool q_pinned = is_device_accessible_host(q_host);
+    const bool t_pinned = tb == 0 || is_device_accessible_host(t_host);
+    if (!q_pinned || !t_pinned) {
+        if ((rc = ensure(&c.pin_in, &c.pin_in_cap, o_d2, true)) != FM_OK) return rc;
+    }
+    const bool out_pinned = is_device_accessible_host(d2_host) && is_device_accessible_host(idx_host) &&
+                            (!dist_host || is_device_accessible_host(dist_host)) &&
+                            (!mask_host || is_device_accessible_host(mask_host));
+    if (!out_pinned && (rc = ensure(&c.pin_out, &c.pin_out_cap, o_ws - o_d2, true)) != FM_OK) return rc;
+
+    *enqueued = true;
+    if (tb) {
+        const uint8_t *src = t_host;
+        if (!t_pinned) { memcpy(c.pin_in + o_t, t_host, tb); src = c.pin_in + o_t; }
+        FM_CUDA_TRY(cudaMemcpyAsync(c.dev + o_t, src, tb, cudaMemcpyHostToDevice, c.copy));
+    }
+    for (int h = 0; h < halves; ++h) {
+        const size_t off = (size_t)hbeg[h] * FM_DIM, nb = (size_t)hm[h] * FM_DIM;
+        const uint8_t *src = q_host + off;
+        if (!q_pinned) { memcpy(c.pin_in + o_q + off, q_host + off, nb); src = c.pin_in + o_q + off; }
+        FM_CUDA_TRY(cudaMemcpyAsync(c.dev + o_q + off, src, nb, cudaMemcpyHostToDevice, c.copy));
+        FM_CUDA_TRY(cudaEventRecord(c.in_ready[h], c.copy));
+    }
+    uint8_t *out_base = out_pinned ? nullptr : c.pin_out;
+    auto dst = [&](void *user, size_t dev_off) -> uint8_t * {
+        return out_pinned ? (uint8_t *)user : out_base + (dev_off - o_d2);
+    };
+    for (int h = 0; h < halves; ++h) {
+        if (hm[h] == 0) continue;
+        const int64_t r0 = hbeg[h], m = hm[h];
+        FM_CUDA_TRY(cudaStreamWaitEvent(c.compute, c.in_ready[h], 0));
+        uint32_t *d2_dev = (uint32_t *)(c.dev + o_d2) + r0 * 2;
+        int32_t *idx_dev = (int32_t *)(c.dev + o_idx) + r0 * 2;
+        if (mask_host)     // Lowe ratio test d1/d2 < tau fused into the same launch sequence
+            rc = fm_ratio_match_u8(c.dev + o_q + r0 * FM_DIM, m, c.dev + o_t, N, tau, d2_dev, idx_dev, nullptr,
+                                   c.dev + o_mask + r0, c.dev + o_ws, wsb, FM_ALGO_AUTO, c.compute);
+        else
+            rc = fm_top2_u8(c.dev + o_q + r0 * FM_DIM, m, c.dev + o_t, N, 0, d2_dev, idx_dev, nullptr,
+                            c.dev + o_ws, wsb, FM_ALGO_AUTO, c.compute);
+        if (rc != FM_OK) return rc;
+        if (dist_host) {
+            k_dist<<<grid_for(m * 2, 256), 256, 0, c.compute>>>(d2_dev, (float *)(c.dev + o_dist) + r0 * 2, m * 2);
+            FM_CUDA_TRY(cudaGetLastError());
+            fm::count_launch();
+        }
+        FM_CUDA_TRY(cudaEventRecord(c.done[h], c.compute));
+        // results of this half go back on the copy stream (which has nothing else left to do once
+        // the inputs are up) while the compute stream works on the other half
+        FM_CUDA_TRY(cudaStreamWaitEvent(c.copy, c.done[h], 0));
+        const size_t r8 = (size_t)r0 * 8, m8 = (size_t)m * 8;
+        FM_CUDA_TRY(cudaMemcpyAsync(dst(d2_host, o_d2) + r8, c.dev + o_d2 + r8, m8, cudaMemcpyDeviceToHost, c.copy));
+        FM_CUDA_TRY(cudaMemcpyAsync(dst(idx_host, o_idx) + r8, c.dev + o_idx + r8, m8, cudaMemcpyDeviceToHost, c.copy));
+        if (dist_host)
+            FM_CUDA_TRY(cudaMemcpyAsync(dst(dist_host, o_dist) + r8, c.dev + o_dist + r8, m8, cudaMemcpyDeviceToHost, c.copy));
+        if (mask_host)
+            FM_CUDA_TRY(cudaMemcpyAsync(dst(mask_host, o_mask) + r0, c.dev + o_mask + r0, (size_t)m, cudaMemcpyDeviceToHost, c.copy));
+    }
+    FM_CUDA_TRY(cudaStreamSynchronize(c.copy));
+    FM_CUDA_TRY(cudaStreamSynchronize(c.compute));
+    *enqueued = false;
+    if (!out_pinned) {
+        memcpy(d2_host, c.pin_out, ob_d2);
+        memcpy(idx_host, c.pin_out + (o_idx - o_d2), ob_idx);
+        if (dist_host) memcpy(dist_host, c.pin_out + (o_dist - o_d2), ob_dist);
+        if (mask_host) memcpy(mask_host, c.pin_out + (o_mask - o_d2), ob_mask);
+    }
+    return FM_OK;
+}
+}  // namespace
 
 int fm_top2_host_u8(const uint8_t *q_host, int64_t M, const uint8_t *t_host, int64_t N,
                     uint32_t *d2_host, int32_t *idx_host, float *dist_host, double tau,
@@ -348,70 +470,26 @@ int fm_top2_host_u8(const uint8_t *q_host, int64_t M, const uint8_t *t_host, int
         set_error("fm_top2_host_u8: bad argument");
         return FM_EINVAL;
     }
+    if (device < 0 || device >= HOST_MAX_DEVICES) {
+        set_error("fm_top2_host_u8: device %d out of range", device);
+        return FM_EINVAL;
+    }
     if (M == 0) return FM_OK;
-    HostCtx &c = g_host;
+    HostCtx &c = g_host[device];                       // per device: calls on different GPUs do not serialise
     std::lock_guard<std::mutex> lock(c.mu);
-    FM_CUDA_TRY(cudaSetDevice(device));
-    if (c.device != device) {
-        if (c.stream) { cudaStreamDestroy(c.stream); c.stream = nullptr; }
-        if (c.dev) { cudaFree(c.dev); c.dev = nullptr; c.dev_cap = 0; }
-        FM_CUDA_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-        c.device = device;
-    }
-    const size_t qb = (size_t)M * FM_DIM, tb = (size_t)N * FM_DIM;
-    const size_t ob_d2 = (size_t)M * 2 * 4, ob_idx = ob_d2, ob_dist = dist_host ? ob_d2 : 0;
-    const size_t ob_mask = mask_host ? (size_t)M : 0;
-    const size_t wsb = fm_top2_workspace_bytes(M, N);
-    // device layout: q | t | d2 | idx | dist | mask | ws
-    const size_t o_q = 0, o_t = up256(qb), o_d2 = o_t + up256(tb), o_idx = o_d2 + up256(ob_d2),
-                 o_dist = o_idx + up256(ob_idx), o_mask = o_dist + up256(ob_dist),
-                 o_ws = o_mask + up256(ob_mask), total = o_ws + up256(wsb);
-    int rc;
-    if ((rc = ensure(&c.dev, &c.dev_cap, total, false)) != FM_OK) return rc;
-    // inputs: pinned / registered host memory is copied straight from the caller's buffer,
-    // pageable memory goes through the library's pinned staging area
-    const bool q_pinned = is_device_accessible_host(q_host);
-    const bool t_pinned = tb == 0 || is_device_accessible_host(t_host);
-    if (!q_pinned || !t_pinned) {
-        if ((rc = ensure(&c.pin_in, &c.pin_in_cap, o_d2, true)) != FM_OK) return rc;
-    }
-    const uint8_t *qsrc = q_host, *tsrc = t_host;
-    if (!q_pinned) { memcpy(c.pin_in + o_q, q_host, qb); qsrc = c.pin_in + o_q; }
-    if (!t_pinned && tb) { memcpy(c.pin_in + o_t, t_host, tb); tsrc = c.pin_in + o_t; }
-    FM_CUDA_TRY(cudaMemcpyAsync(c.dev + o_q, qsrc, qb, cudaMemcpyHostToDevice, c.stream));
-    if (tb) FM_CUDA_TRY(cudaMemcpyAsync(c.dev + o_t, tsrc, tb, cudaMemcpyHostToDevice, c.stream));
-    uint32_t *d2_dev = (uint32_t *)(c.dev + o_d2);
-    if (mask_host)     // Lowe ratio test d1/d2 < tau fused into the same launch sequence
-        rc = fm_ratio_match_u8(c.dev + o_q, M, c.dev + o_t, N, tau, d2_dev, (int32_t *)(c.dev + o_idx),
-                               nullptr, c.dev + o_mask, c.dev + o_ws, up256(wsb), FM_ALGO_AUTO, c.stream);
-    else
-        rc = fm_top2_u8(c.dev + o_q, M, c.dev + o_t, N, 0, d2_dev, (int32_t *)(c.dev + o_idx), nullptr,
-                        c.dev + o_ws, up256(wsb), FM_ALGO_AUTO, c.stream);
+    DeviceGuard guard;
+    int rc = guard.enter(device);
     if (rc != FM_OK) return rc;
-    if (dist_host) {
-        k_dist<<<grid_for(M * 2, 256), 256, 0, c.stream>>>(d2_dev, (float *)(c.dev + o_dist), M * 2);
-        FM_CUDA_TRY(cudaGetLastError());
-        fm::count_launch();
+    bool enqueued = false;
+    rc = top2_host_locked(c, q_host, M, t_host, N, d2_host, idx_host, dist_host, tau, mask_host, &enqueued);
+    if (enqueued) {
+        // an error after work was queued: drain both streams so that the staging buffers are not
+        // reused (or the caller's buffers freed) under a copy that is still in flight
+        cudaStreamSynchronize(c.copy);
+        cudaStreamSynchronize(c.compute);
+        (void)cudaGetLastError();
     }
-    const bool out_pinned = is_device_accessible_host(d2_host) && is_device_accessible_host(idx_host) &&
-                            (!dist_host || is_device_accessible_host(dist_host)) &&
-                            (!mask_host || is_device_accessible_host(mask_host));
-    if (out_pinned) {
-        FM_CUDA_TRY(cudaMemcpyAsync(d2_host, c.dev + o_d2, ob_d2, cudaMemcpyDeviceToHost, c.stream));
-        FM_CUDA_TRY(cudaMemcpyAsync(idx_host, c.dev + o_idx, ob_idx, cudaMemcpyDeviceToHost, c.stream));
-        if (dist_host) FM_CUDA_TRY(cudaMemcpyAsync(dist_host, c.dev + o_dist, ob_dist, cudaMemcpyDeviceToHost, c.stream));
-        if (mask_host) FM_CUDA_TRY(cudaMemcpyAsync(mask_host, c.dev + o_mask, ob_mask, cudaMemcpyDeviceToHost, c.stream));
-        FM_CUDA_TRY(cudaStreamSynchronize(c.stream));
-        return FM_OK;
-    }
-    if ((rc = ensure(&c.pin_out, &c.pin_out_cap, o_ws - o_d2, true)) != FM_OK) return rc;
-    FM_CUDA_TRY(cudaMemcpyAsync(c.pin_out, c.dev + o_d2, o_ws - o_d2, cudaMemcpyDeviceToHost, c.stream));
-    FM_CUDA_TRY(cudaStreamSynchronize(c.stream));
-    memcpy(d2_host, c.pin_out, ob_d2);
-    memcpy(idx_host, c.pin_out + (o_idx - o_d2), ob_idx);
-    if (dist_host) memcpy(dist_host, c.pin_out + (o_dist - o_d2), ob_dist);
-    if (mask_host) memcpy(mask_host, c.pin_out + (o_mask - o_d2), ob_mask);
-    return FM_OK;
+    return rc;
 }
 
 }  // extern "C"

@@ -22,6 +22,8 @@
 // "<", so ties go to the lowest local index exactly as cv::batchDistance does.
 #include <cuda.h>
 
+#include <mutex>
+
 #include "fm_common.cuh"
 #include "fm_tc_ptx.cuh"
 
@@ -545,14 +547,22 @@ int launch_grouped_tc(const uint8_t *qpool, const int32_t *q_gather, const int64
         int rc;
         if ((rc = make_map(&map_q, qpack ? qpack : qpool, total_q, FM_DIM, BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
         if ((rc = make_map(&map_t, tpool, tpool_rows, FM_DIM, BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
-        static bool attr_set = false;
-        if (!attr_set) {
-            FM_CUDA_TRY(cudaFuncSetAttribute(k_grouped_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
-            attr_set = true;
-        }
+        // function attributes and SM counts are per device: a process may drive several GPUs
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        static std::mutex attr_mu;
+        static bool attr_set[64] = {};
+        static int sm_count[64] = {};
+        {
+            std::lock_guard<std::mutex> lock(attr_mu);
+            const int slot = dev >= 0 && dev < 64 ? dev : 0;
+            if (!attr_set[slot] || slot != dev) {
+                FM_CUDA_TRY(cudaFuncSetAttribute(k_grouped_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
+                cudaDeviceGetAttribute(&sm_count[slot], cudaDevAttrMultiProcessorCount, dev);
+                attr_set[slot] = true;
+            }
+            if (sm_count[slot] > 0) sms = sm_count[slot];
+        }
         Params P{q_off, t_off, t_base, qnorm, tnorm, G, counter, q2t_d2, q2t_idx, t2q_idx};
         const int grid = G < sms ? G : sms;
         prof_begin(s);

@@ -34,6 +34,9 @@
 //     (partial*256 + column) and update the row's top-2 with strict "<" in increasing column
 //     order, so ties keep the lowest index.  Results are exact for any u8 input.
 #include <cuda.h>
+#include <math.h>
+
+#include <mutex>
 
 #include "fm_common.cuh"
 #include "fm_tc_ptx.cuh"
@@ -84,6 +87,13 @@ constexpr int NONE_P = 0x7FFFFF;   // "no candidate": above every real partial d
 //   i.e. mean byte value > 174, just get E_j = 0: the filter stays conservative, never wrong).
 //   ckey_j = (|t_j|^2 + 2 E_j) * 256 + (j & 255)  (wrapping int32; INT_MAX on the tile padding).
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: the three kernels of a call (pre-pass, sweep, slot merge) are
+// chained so that each one is scheduled -- and runs its prologue -- while its predecessor drains;
+// pdl_wait() returns once the predecessor has completed and its writes are visible (no-op for a
+// kernel that was launched without the attribute).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int EHALF_MAX = 255 * 255 * 15 + 254;   // digits 0..14 weigh 255, digit 15 weighs 1
 constexpr int EMAX = 2 * EHALF_MAX;
 constexpr int CG = 2 * EMAX;                      // the constant C of the filter
@@ -91,6 +101,7 @@ __global__ void k_prepass(const uint8_t *__restrict__ q, int64_t M, int64_t m_pa
                           const uint8_t *__restrict__ t, int64_t N, int64_t n_padded,
                           int *__restrict__ qn, int *__restrict__ gbound, int *__restrict__ ckey,
                           uint4 *__restrict__ digits) {
+    pdl_launch_dependents();                      // the sweep may be scheduled; it waits before it reads
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t row = gt >> 3;                  // 8 threads (16 B each) per descriptor
     const int sub = (int)(gt & 7);
@@ -138,19 +149,37 @@ __global__ void k_prepass(const uint8_t *__restrict__ q, int64_t M, int64_t m_pa
 // ---------------------------------------------------------------------------------------------
 #ifdef FM_TC_PROF
 __device__ unsigned long long g_prof[16];
+__device__ unsigned long long g_tl[160 * 8];      // per CTA: globaltimer stamps of the kernel's phases
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 #define PROF_T0() const long long _t0 = clock64()
 #define PROF_ADD(slot) _pacc[slot] += (unsigned long long)(clock64() - _t0)
+#define TL_STAMP(slot) do { if (blockIdx.x < 160) g_tl[blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
 #else
 #define PROF_T0()
 #define PROF_ADD(slot)
+#define TL_STAMP(slot)
 #endif
 
-// first CTA of a `grid`-CTA launch whose work range [work*c/grid, work*(c+1)/grid) holds `step`
-__host__ __device__ __forceinline__ long long cta_of_step(long long step, long long work, long long grid) {
-    long long c = step * grid / work;
-    while (work * (c + 1) / grid <= step) ++c;
-    while (c > 0 && work * c / grid > step) --c;
-    return c;
+// The persistent schedule: worker w owns the (M-block, tile) steps [begin[w], begin[w + 1]) of the
+// M-block-major step sequence.  The host cuts the sequence by a cost model (make_plan), so the
+// ranges travel as a kernel parameter.
+constexpr int MAX_WORKERS = 160;
+struct Sched {
+    long long begin[MAX_WORKERS + 1];
+};
+
+// the worker whose range holds `step` (largest w with begin[w] <= step; ranges are never empty)
+__host__ __device__ __forceinline__ int owner_of_step(const Sched &sc, int nworkers, long long step) {
+    int lo = 0, hi = nworkers - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (sc.begin[mid] <= step) lo = mid; else hi = mid - 1;
+    }
+    return lo;
 }
 
 // A CTA's work range as a sequence of segments: runs of target tiles of one M-block.  Only the
@@ -252,7 +281,7 @@ static_assert(Cfg<true>::STAGES <= 8 && STAGES <= 8, "Bars holds 8 ring slots");
 template <bool PAIR>
 __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUtensorMap &map_t,
                                             const CUtensorMap &map_x, int64_t M, int64_t N,
-                                            int32_t t_index_base, int ntiles_row, long long work_total, int aligned,
+                                            int32_t t_index_base, int ntiles_row, const Sched &sched,
                                             const int *__restrict__ qn, const int *__restrict__ ckey,
                                             int *__restrict__ gbound,
                                             unsigned long long *__restrict__ partial) {
@@ -260,6 +289,7 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
 #ifdef FM_TC_PROF
     const long long _tk0 = clock64();
     unsigned long long _pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (threadIdx.x == 0) TL_STAMP(0);
 #endif
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -276,18 +306,13 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
     const unsigned nworkers = PAIR ? gridDim.x >> 1 : gridDim.x;
     Segments seg0;
     {
-        // `aligned`: whole M-blocks per worker instead (every worker starts at tile 0 and they sweep
-        // the targets in step -- chosen by the host when the targets do not fit L2)
-        const long long units = aligned ? work_total / ntiles_row : work_total;
-        const long long scale = aligned ? ntiles_row : 1;
-        const long long w_begin = units * worker / nworkers * scale;
-        const long long w_end = units * (worker + 1) / nworkers * scale;
+        const long long w_begin = sched.begin[worker], w_end = sched.begin[worker + 1];
         seg0.ntiles_row = ntiles_row;
         seg0.mblock = (int)(w_begin / ntiles_row);
         seg0.tile_begin = (int)(w_begin - (long long)seg0.mblock * ntiles_row);
         seg0.remaining = (int)(w_end - w_begin);          // < 2^31: checked by the host
         seg0.slot = seg0.tile_begin == 0 ? 0
-            : (int)(worker - cta_of_step(w_begin - seg0.tile_begin, work_total, nworkers));
+            : (int)worker - owner_of_step(sched, (int)nworkers, w_begin - seg0.tile_begin);
     }
 
     if (threadIdx.x == 0) {
@@ -319,6 +344,11 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
+    // everything above overlapped the pre-pass; its outputs (digits, key constants, norms, bounds)
+    // are read from here on
+    pdl_wait();
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) TL_STAMP(1);
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -391,7 +421,7 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
             int u = 0;
             Segments sg = seg0;
             for (int seg = 0; sg.more(); ++seg, sg.advance()) {
-                mbar_wait(smem_u32(&bars->a_full), seg & 1);
+                { PROF_T0(); mbar_wait(smem_u32(&bars->a_full), seg & 1); PROF_ADD(3); }
                 tc_fence_after();
                 const int nt = sg.ntiles();
                 for (int it = 0; it < nt; ++it, ++u) {
@@ -399,6 +429,9 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
                     const uint32_t ph = (u / C::STAGES) & 1;
                     { PROF_T0(); mbar_wait(smem_u32(&bars->full[stage]), ph); PROF_ADD(0); }
                     tc_fence_after();
+#ifdef FM_TC_PROF
+                    if (u == 0 && lane == 0) TL_STAMP(2);
+#endif
                     const uint32_t sb = sbase + SMEM_B + stage * C::STAGE_BYTES;
 #pragma unroll
                     for (int b = 0; b < C::NBUF; ++b) {
@@ -436,6 +469,9 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
                 if (elect_one()) commit(smem_u32(&bars->a_empty));      // the query tile may be replaced
                 __syncwarp();
             }
+#ifdef FM_TC_PROF
+            if (lane == 0) TL_STAMP(3);
+#endif
         }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
@@ -508,6 +544,7 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
             mbar_wait(full_a, u & 1);
 #ifdef FM_TC_PROF
             const long long _te1 = clock64();
+            if (u == 0 && warp == 4 && lane == 0) TL_STAMP(4);
 #endif
             tc_fence_after();
             // The last accumulator of a tile being complete means every MMA that read the tile's
@@ -589,6 +626,9 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
             }
         }
         }   // segments
+#ifdef FM_TC_PROF
+        if (warp == 4 && lane == 0) TL_STAMP(5);
+#endif
     }
 
     tc_fence_before();
@@ -599,7 +639,7 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
 #ifdef FM_TC_PROF
     if ((threadIdx.x & 31) == 0)
         for (int i = 0; i < 8; ++i) if (_pacc[i]) atomicAdd(&g_prof[i], _pacc[i]);
-    if (threadIdx.x == 0) { atomicAdd(&g_prof[8], (unsigned long long)(clock64() - _tk0)); atomicAdd(&g_prof[9], 1ull); atomicAdd(&g_prof[10], (unsigned long long)seg0.remaining); }
+    if (threadIdx.x == 0) { atomicAdd(&g_prof[8], (unsigned long long)(clock64() - _tk0)); atomicAdd(&g_prof[9], 1ull); atomicAdd(&g_prof[10], (unsigned long long)seg0.remaining); TL_STAMP(6); }
 #endif
     if (warp == 2) {
         tc_fence_after();
@@ -611,32 +651,32 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_top2_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
           const __grid_constant__ CUtensorMap map_x, int64_t M, int64_t N, int32_t t_index_base,
-          int ntiles_row, long long work_total, int aligned, const int *__restrict__ qn,
+          int ntiles_row, const __grid_constant__ Sched sched, const int *__restrict__ qn,
           const int *__restrict__ ckey, int *__restrict__ gbound,
           unsigned long long *__restrict__ partial) {
-    k_top2_body<false>(map_q, map_t, map_x, M, N, t_index_base, ntiles_row, work_total, aligned, qn, ckey, gbound, partial);
+    k_top2_body<false>(map_q, map_t, map_x, M, N, t_index_base, ntiles_row, sched, qn, ckey, gbound, partial);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 k_top2_tc_pair(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t,
                const __grid_constant__ CUtensorMap map_x, int64_t M, int64_t N, int32_t t_index_base,
-               int ntiles_row, long long work_total, int aligned, const int *__restrict__ qn,
+               int ntiles_row, const __grid_constant__ Sched sched, const int *__restrict__ qn,
                const int *__restrict__ ckey, int *__restrict__ gbound,
                unsigned long long *__restrict__ partial) {
-    k_top2_body<true>(map_q, map_t, map_x, M, N, t_index_base, ntiles_row, work_total, aligned, qn, ckey, gbound, partial);
+    k_top2_body<true>(map_q, map_t, map_x, M, N, t_index_base, ntiles_row, sched, qn, ckey, gbound, partial);
 }
 
 // merge of the partial keys the CTAs that swept one M-block left in its slots (same semantics as
 // fm_merge_top2); the slot count of a block follows from the schedule.
 __global__ void k_merge_partial(const unsigned long long *__restrict__ partial, int ntiles_row,
-                                long long work_total, int grid, int aligned, int mblock_rows, int64_t M,
+                                const __grid_constant__ Sched sched, int nworkers, int mblock_rows, int64_t M,
                                 uint32_t *__restrict__ d2, int32_t *__restrict__ idx,
                                 unsigned long long *__restrict__ keys, const RatioOut rout) {
+    pdl_wait();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= M) return;
     const long long first = (i / mblock_rows) * ntiles_row;
-    const int slots = aligned ? 1 : (int)(cta_of_step(first + ntiles_row - 1, work_total, grid) -
-                                          cta_of_step(first, work_total, grid)) + 1;
+    const int slots = owner_of_step(sched, nworkers, first + ntiles_row - 1) - owner_of_step(sched, nworkers, first) + 1;
     unsigned long long a = FM_NONE_KEY, b = FM_NONE_KEY;
     for (int s = 0; s < slots; ++s) {
         const ulonglong2 v = *(const ulonglong2 *)(partial + ((int64_t)s * M + i) * 2);
@@ -666,29 +706,47 @@ struct Plan {
     int64_t mblocks, mpad, ntiles, npad, work;
     int workers, slots;         // CTAs (or pairs) in the persistent grid; partial-key slots per row
     int aligned;                // whole M-blocks per worker (targets larger than L2)
+    Sched sched;                // first step of every worker
     size_t off_ckey, off_digits, off_qn, off_gbound, off_partial, total;
 };
 
-static int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
+// Per-device facts and one-time set-up, keyed by the current device: a process may drive several
+// GPUs, and function attributes / SM counts / cluster support are per device.
+struct DevInfo {
+    bool init = false, attrs_set = false;
+    int sms = 148, major = 0, pair_ok = 0;
+    size_t l2 = 64u << 20;
+};
+constexpr int MAX_DEVICES = 64;
+static DevInfo &dev_info() {
+    static DevInfo info[MAX_DEVICES];
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) dev = 0;
+    DevInfo &d = info[dev];
+    std::lock_guard<std::mutex> lock(mu);
+    if (!d.init) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) d.sms = v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev) == cudaSuccess && v > 0) d.l2 = (size_t)v;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess) d.major = v;
+        // Can a 2-CTA cluster of the pair kernel be resident at all (it cannot on e.g. a MIG slice
+        // with single-SM TPCs)?  "No" or any error selects the single-CTA kernel.
+        if (d.major == 10 &&
+            cudaFuncSetAttribute(k_top2_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC) == cudaSuccess &&
+            cudaFuncSetAttribute(k_top2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC) == cudaSuccess) {
+            d.attrs_set = true;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2);
+            cfg.blockDim = dim3(NTHREADS);
+            cfg.dynamicSmemBytes = SMEM_ALLOC;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, k_top2_tc_pair, &cfg) == cudaSuccess && n > 0) d.pair_ok = 1;
+        }
+        (void)cudaGetLastError();
+        d.init = true;
     }
-    return n;
-}
-
-static size_t l2_bytes() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrL2CacheSize, dev);
-        if (n <= 0) n = 64 << 20;
-    }
-    return (size_t)n;
+    return d;
 }
 
 // FM_TC_PAIR=0 / 1 forces the single-CTA / CTA-pair kernel (for A/B timing and tests); default: pair
@@ -703,50 +761,84 @@ static int pair_override() {
     return v;
 }
 
-// Can a 2-CTA cluster of the pair kernel be resident at all (it cannot on e.g. a MIG slice with
-// single-SM TPCs)?  Asked once; "no" or any error selects the single-CTA kernel.
-static bool pair_available() {
-    static int ok = -1;
-    if (ok < 0) {
-        ok = 0;
-        if (cudaFuncSetAttribute(k_top2_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC) == cudaSuccess) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(2);
-            cfg.blockDim = dim3(NTHREADS);
-            cfg.dynamicSmemBytes = SMEM_ALLOC;
-            int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, k_top2_tc_pair, &cfg) == cudaSuccess && n > 0) ok = 1;
+// Cost model of the stream-K cut (measured with tools/timeline.py): besides one unit per tile step a
+// worker pays for every exact update of a row's top-2 ("event", ~0.1 tile steps each), and those
+// concentrate where a row is swept first.  A block's steps that run at the start of a worker's range
+// -- the tail piece [x, L) of a split block, or a whole block -- start from no bound at all:
+//   events(s tiles) = 8 s for s < 4, else 32 + 64 ln(s / 4)   (per warp: 32 rows x 2 ln(targets))
+// while the head piece [0, x) of a split block runs at the very end of the previous worker's range,
+// seeded through `gbound` by the tail piece that ran first, and only pays the remainder.  So the cost
+// of the step sequence up to tile x of a block is  head(x) = block_cost - tail_cost(L - x), and the
+// cuts are placed at equal increments of that cumulative cost.
+static double tail_cost(double s, double evcost) {
+    if (s <= 0) return 0;
+    return s + evcost * (s < 4 ? 8 * s : 32 + 64 * log(s / 4));
+}
+
+static void cut_schedule(Plan &p, double evcost) {
+    const int W = p.workers;
+    const long long L = p.ntiles;
+    if (p.aligned) {
+        for (int w = 0; w <= W; ++w) p.sched.begin[w] = p.mblocks * w / W * L;
+    } else {
+        const double cb = tail_cost((double)L, evcost), total = cb * (double)p.mblocks;
+        p.sched.begin[0] = 0;
+        for (int w = 1; w < W; ++w) {
+            const double c = total * w / W;
+            long long blk = (long long)(c / cb);
+            if (blk >= p.mblocks) blk = p.mblocks - 1;
+            const double rem = c - blk * cb;
+            long long lo = 0, hi = L;           // smallest x with head(x) >= rem
+            while (lo < hi) {
+                const long long mid = (lo + hi) >> 1;
+                if (cb - tail_cost((double)(L - mid), evcost) >= rem) hi = mid; else lo = mid + 1;
+            }
+            p.sched.begin[w] = blk * L + lo;
         }
-        (void)cudaGetLastError();
+        p.sched.begin[W] = p.work;
+        for (int w = 1; w < W; ++w)             // never an empty range
+            if (p.sched.begin[w] <= p.sched.begin[w - 1]) p.sched.begin[w] = p.sched.begin[w - 1] + 1;
+        for (int w = W - 1; w >= 1; --w)
+            if (p.sched.begin[w] >= p.sched.begin[w + 1]) p.sched.begin[w] = p.sched.begin[w + 1] - 1;
     }
-    return ok == 1;
+    for (int w = W + 1; w <= MAX_WORKERS; ++w) p.sched.begin[w] = p.work;
+    // partial-key slots: only a worker's first run can start inside an M-block
+    int slots = 1;
+    for (int w = 1; w < W; ++w) {
+        const long long b = p.sched.begin[w];
+        if (b % L == 0) continue;
+        const int slot = w - owner_of_step(p.sched, W, b - b % L);
+        if (slot + 1 > slots) slots = slot + 1;
+    }
+    p.slots = slots;
 }
 
 static Plan make_plan(int64_t M, int64_t N) {
     Plan p;
+    const DevInfo &dv = dev_info();
     const int ov = pair_override();
     // pair by default unless its 512-row M-blocks would add a (relatively) large block of padding
     p.pair = (ov >= 0 ? ov != 0 : (M > 8 * SUBS * BM || (M > SUBS * BM && (M - 1) % (2 * SUBS * BM) >= SUBS * BM))) &&
-             pair_available();
+             dv.pair_ok;
     p.mblock_rows = p.pair ? 2 * SUBS * BM : SUBS * BM;
     p.mblocks = (M + p.mblock_rows - 1) / p.mblock_rows;
     p.mpad = p.mblocks * p.mblock_rows;
     p.ntiles = (N + BN - 1) / BN;
     p.npad = p.ntiles * BN;
-    // persistent grid: every worker gets an equal, contiguous share of the (M-block, tile) steps
+    // persistent grid: every worker gets a contiguous share of the (M-block, tile) steps
     p.work = p.mblocks * p.ntiles;
-    const int cap = p.pair ? sm_count() / 2 : sm_count();
+    int cap = p.pair ? dv.sms / 2 : dv.sms;
+    if (cap > MAX_WORKERS) cap = MAX_WORKERS;
     p.workers = (int)(p.work < cap ? p.work : cap);
     if (p.workers < 1) p.workers = 1;
     // Targets (+ digits) that do not fit L2 are streamed from HBM once per M-block unless the workers
     // sweep them in step: give every worker whole M-blocks then (<= 1/8 imbalance by the condition).
     static const int aligned_override = [] { const char *e = getenv("FM_TC_ALIGNED"); return e && *e ? atoi(e) : -1; }();
     p.aligned = aligned_override >= 0 ? aligned_override != 0
-        : (size_t)p.npad * (FM_DIM + 32) > l2_bytes() / 2 && p.mblocks >= 8 * (int64_t)p.workers;
-    const int64_t per_worker = p.work / p.workers;               // >= 1: the shortest range
-    int64_t slots = (p.ntiles + per_worker - 1) / per_worker + 1;  // workers that can touch one M-block
-    if (slots > p.workers) slots = p.workers;
-    p.slots = p.aligned ? 1 : (int)slots;
+        : (size_t)p.npad * (FM_DIM + 32) > dv.l2 / 2 && p.mblocks >= 8 * (int64_t)p.workers;
+    if (p.aligned && p.mblocks < p.workers) p.aligned = 0;       // (forced by the override on a small problem)
+    static const double evcost = [] { const char *e = getenv("FM_TC_EVCOST"); return e && *e ? atof(e) : 0.15; }();
+    cut_schedule(p, evcost);
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     p.off_ckey = 0;
     p.off_digits = up(p.off_ckey + (size_t)p.npad * 4);
@@ -766,6 +858,11 @@ extern "C" int fm_debug_prof(unsigned long long *out16, int reset) {
     if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tc::g_prof, z, sizeof(z)); }
     return 0;
 }
+// globaltimer stamps of the last launch: out[cta * 8 + phase], 160 CTAs
+extern "C" int fm_debug_timeline(unsigned long long *out1280) {
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out1280, tc::g_tl, sizeof(unsigned long long) * 160 * 8) == cudaSuccess ? 0 : -1;
+}
 #endif
 
 // Test hook (not part of include/fastmatch_b200.h): the schedule the dense tcgen05 kernel would use.
@@ -778,15 +875,19 @@ extern "C" int fm_debug_plan(int64_t M, int64_t N, long long *out8) {
     return FM_OK;
 }
 
+// Test hook: first step of every worker of that schedule; out[0..workers] (cap >= workers + 1).
+extern "C" int fm_debug_plan_begins(int64_t M, int64_t N, long long *out, int cap) {
+    if (M <= 0 || N <= 0 || out == nullptr) return FM_EINVAL;
+    const tc::Plan p = tc::make_plan(M, N);
+    if (cap < p.workers + 1) return FM_ENOSPACE;
+    for (int w = 0; w <= p.workers; ++w) out[w] = p.sched.begin[w];
+    return FM_OK;
+}
+
 bool tc_supported() {
-    static int ok = -1;
-    if (ok < 0) {
-        int dev = 0, major = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return false;
-        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-        ok = (major == 10 && tc::encode_fn() != nullptr) ? 1 : 0;
-    }
-    return ok == 1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return tc::dev_info().major == 10 && tc::encode_fn() != nullptr;
 }
 
 size_t top2_tc_workspace_bytes(int64_t M, int64_t N) {
@@ -811,7 +912,11 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     }
     const Plan p = make_plan(M, N);
     if (ws_bytes < p.total) { set_error("tcgen05 path: workspace too small"); return FM_ENOSPACE; }
-    if (p.work / p.workers >= (int64_t)0x7FFFFFF0) { set_error("tcgen05 path: M x N too large for one launch, shard it"); return FM_EINVAL; }
+    for (int w = 0; w < p.workers; ++w)
+        if (p.sched.begin[w + 1] - p.sched.begin[w] >= (long long)0x7FFFFFF0) {
+            set_error("tcgen05 path: M x N too large for one launch, shard it");
+            return FM_EINVAL;
+        }
     uint8_t *w = (uint8_t *)ws;
     int *ckey = (int *)(w + p.off_ckey), *qn = (int *)(w + p.off_qn);
     uint8_t *digits = w + p.off_digits;
@@ -831,27 +936,36 @@ int launch_top2_tc(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, int
     FM_CUDA_TRY(cudaGetLastError());
     count_launch();
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        FM_CUDA_TRY(cudaFuncSetAttribute(k_top2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
-        FM_CUDA_TRY(cudaFuncSetAttribute(k_top2_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_ALLOC));
-        attr_set = true;
-    }
+    if (!dev_info().attrs_set) { set_error("tcgen05 path: could not opt in to %d bytes of shared memory", SMEM_ALLOC); return FM_ECUDA; }
+    // FM_TC_PDL=0 launches the three kernels back to back without programmatic dependent launch
+    static const bool use_pdl = [] { const char *e = getenv("FM_TC_PDL"); return !(e && *e && atoi(e) == 0); }();
+    cudaLaunchAttribute pdl_attr[1];
+    pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = s;
+    cfg.attrs = pdl_attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_ALLOC;
+    const int ntiles_i = (int)p.ntiles;
     prof_begin(s);
-    if (p.pair)
-        k_top2_tc_pair<<<2 * p.workers, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base,
-                                                                   (int)p.ntiles, (long long)p.work, p.aligned, qn,
-                                                                   ckey, gbound, partial);
-    else
-        k_top2_tc<<<p.workers, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, map_x, M, N, t_index_base, (int)p.ntiles,
-                                                          (long long)p.work, p.aligned, qn, ckey, gbound, partial);
+    if (p.pair) {
+        cfg.gridDim = dim3(2 * p.workers);
+        FM_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_top2_tc_pair, map_q, map_t, map_x, M, N, t_index_base, ntiles_i, p.sched,
+                                       (const int *)qn, (const int *)ckey, gbound, partial));
+    } else {
+        cfg.gridDim = dim3(p.workers);
+        FM_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_top2_tc, map_q, map_t, map_x, M, N, t_index_base, ntiles_i, p.sched,
+                                       (const int *)qn, (const int *)ckey, gbound, partial));
+    }
     prof_end(s);
-    FM_CUDA_TRY(cudaGetLastError());
     count_launch();
-    k_merge_partial<<<(unsigned)((M + 255) / 256), 256, 0, s>>>(partial, (int)p.ntiles, (long long)p.work,
-                                                                p.workers, p.aligned, p.mblock_rows, M, d2, idx,
-                                                                (unsigned long long *)keys, rout);
-    FM_CUDA_TRY(cudaGetLastError());
+    cfg.gridDim = dim3((unsigned)((M + 255) / 256));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    FM_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_merge_partial, (const unsigned long long *)partial, ntiles_i, p.sched,
+                                   p.workers, p.mblock_rows, M, d2, idx, (unsigned long long *)keys, rout));
     count_launch();
     return FM_OK;
 }

@@ -2,6 +2,7 @@
 reports through its test hook is replayed in Python -- every worker's runs of tiles cover the
 (M-block, tile) steps exactly once, slot indices stay inside the partial-key buffer the plan sizes,
 and the number of slots the merge reads per M-block equals the number of workers that wrote one."""
+import bisect
 import ctypes
 
 import pytest
@@ -9,14 +10,17 @@ import pytest
 from fast_match_b200 import backend
 
 
-def cta_of_step(step, work, grid):
-    """First worker whose range [work*c//grid, work*(c+1)//grid) holds `step` (fm_tc.cu)."""
-    c = step * grid // work
-    while work * (c + 1) // grid <= step:
-        c += 1
-    while c > 0 and work * c // grid > step:
-        c -= 1
-    return c
+def owner_of_step(begins, step):
+    """The worker whose range [begins[w], begins[w+1]) holds `step` (owner_of_step in fm_tc.cu)."""
+    return bisect.bisect_right(begins, step) - 1
+
+
+def plan_begins(M, N, workers):
+    out = (ctypes.c_longlong * (workers + 1))()
+    L = backend.lib()
+    L.fm_debug_plan_begins.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]
+    assert L.fm_debug_plan_begins(M, N, out, workers + 1) == 0
+    return list(out)
 
 
 def plan(M, N):
@@ -42,18 +46,21 @@ def test_stream_k_partition(M, N):
     assert 1 <= W <= work
     covered = 0
     writers = {}
+    begins = plan_begins(M, N, W)
+    assert begins[0] == 0 and begins[W] == work and all(b > a for a, b in zip(begins, begins[1:]))
+    sizes = [b - a for a, b in zip(begins, begins[1:])]
+    assert max(sizes) <= 1.25 * work / W + 32            # the cost model only nudges an equal split
     for w in range(W):
+        lo, hi = begins[w], begins[w + 1]
         if p["aligned"]:
-            lo, hi = mblocks * w // W * ntiles, mblocks * (w + 1) // W * ntiles
-        else:
-            lo, hi = work * w // W, work * (w + 1) // W
+            assert lo % ntiles == 0 and hi % ntiles == 0
         assert hi - lo < 2 ** 31
         step = lo
         first = True
         while step < hi:
             m, tb = divmod(step, ntiles)
             nt = min(hi - step, ntiles - tb)
-            slot = 0 if tb == 0 else w - cta_of_step(step - tb, work, W)
+            slot = 0 if tb == 0 else w - owner_of_step(begins, step - tb)
             assert first or tb == 0                      # only the first run starts inside an M-block
             assert 0 <= slot < p["slots"], (w, m, slot)
             assert slot not in writers.setdefault(m, set())
@@ -64,7 +71,7 @@ def test_stream_k_partition(M, N):
     assert covered == work
     for m in ([0, mblocks - 1] if mblocks > 4000 else range(mblocks)):
         f = m * ntiles
-        n = 1 if p["aligned"] else cta_of_step(f + ntiles - 1, work, W) - cta_of_step(f, work, W) + 1
+        n = owner_of_step(begins, f + ntiles - 1) - owner_of_step(begins, f) + 1
         assert writers[m] == set(range(n)), (m, writers[m], n)   # what k_merge_partial reads
     assert p["ws_kib"] * 1024 >= p["slots"] * M * 16
 

@@ -37,12 +37,21 @@ def _worker(rank, world, port, q, t, out):
         keys = sharded.sharded_top2(torch.from_numpy(q), torch.from_numpy(t[lo:hi]), lo,
                                     local_top2=local_top2, merge=merge)
         out[rank] = keys.numpy().view(np.uint64).copy()
+        # the all-to-all exchange: this rank merges only its slice of the queries
+        (q_lo, q_hi), sl = sharded.sharded_top2_sliced(torch.from_numpy(q), torch.from_numpy(t[lo:hi]), lo,
+                                                       local_top2=local_top2, merge=merge)
+        assert (q_lo, q_hi) == sharded.shard_range(len(q), rank, world)
+        out[("slice", rank)] = (q_lo, q_hi, sl.numpy().view(np.uint64).copy())
+        full = sharded.gather_full(sl, len(q))
+        out[("full", rank)] = full.numpy().view(np.uint64).copy()
+        flags = sharded.gather_full(torch.arange(q_lo, q_hi) % 3 == 0, len(q))
+        assert flags.dtype == torch.bool and torch.equal(flags, torch.arange(len(q)) % 3 == 0)
     finally:
         dist.destroy_process_group()
 
 
 def test_two_rank_sharded_top2_equals_unsharded():
-    q, t = synth.make_pair(700, 901, seed=5)
+    q, t = synth.make_pair(701, 901, seed=5)          # odd: the two query slices differ in length
     t[10:20] = t[600:610]                      # ties that straddle the shard boundary
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -53,3 +62,7 @@ def test_two_rank_sharded_top2_equals_unsharded():
     d2, idx = oracle.c_top2(q, t)
     want = oracle.pack_keys(d2, idx)
     assert np.array_equal(out[0], want) and np.array_equal(out[1], want)
+    for r in (0, 1):
+        q_lo, q_hi, sl = out[("slice", r)]
+        assert np.array_equal(sl, want[q_lo:q_hi])
+        assert np.array_equal(out[("full", r)], want)
