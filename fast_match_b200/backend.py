@@ -82,15 +82,29 @@ def device_caps(device=0):
 _ws_cache = {}
 
 
+_WS_MAX_ENTRIES = 16
+
+
 def _workspace(device, nbytes):
-    """Grow-only scratch per (device, stream): reuse is stream-ordered."""
+    """Grow-only scratch per (device, stream): reuse is stream-ordered.  The cache is bounded: when
+    more than _WS_MAX_ENTRIES (device, stream) pairs have been seen, the oldest entry is dropped
+    (torch's caching allocator keeps the block alive until the work queued on it has run)."""
     nbytes = max(int(nbytes), 16)
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    ws = _ws_cache.get(key)
+    ws = _ws_cache.pop(key, None)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            ws.record_stream(torch.cuda.current_stream(device))
         ws = torch.empty(nbytes + nbytes // 4, dtype=torch.uint8, device=device)
-        _ws_cache[key] = ws
+    _ws_cache[key] = ws                      # re-inserted last: dict order = least recently used first
+    while len(_ws_cache) > _WS_MAX_ENTRIES:
+        _ws_cache.pop(next(iter(_ws_cache)))
     return ws
+
+
+def release_workspaces():
+    """Drop every cached scratch buffer (they are re-created on demand)."""
+    _ws_cache.clear()
 
 
 def top2(q, t, t_index_base=0, algo=FM_ALGO_AUTO, want_keys=False, out=None):

@@ -13,7 +13,7 @@ Geometry, persistence and the BallTree radius lookup are host glue and stay on t
 """
 import hashlib
 import os
-import pickle
+import struct
 
 import numpy
 import torch
@@ -111,6 +111,54 @@ class Grid_Cache(object):
 #########################################
 #             Metric Cache              #
 #########################################
+def _ripemd160(data):
+    """RIPEMD-160 (the reference names its cache files RIPEMD-160(path), cache.pyx:193, 216).
+    OpenSSL 3 builds often ship without it, and a different digest would silently miss every cache
+    file the reference wrote, so a pure-Python fallback is used when hashlib has none."""
+    try:
+        return hashlib.new("ripemd160", data).hexdigest()
+    except ValueError:
+        pass
+    rol = lambda x, n: ((x << n) | (x >> (32 - n))) & 0xFFFFFFFF
+    f = [lambda x, y, z: x ^ y ^ z, lambda x, y, z: (x & y) | (~x & 0xFFFFFFFF & z),
+         lambda x, y, z: (x | (~y & 0xFFFFFFFF)) ^ z, lambda x, y, z: (x & z) | (y & ~z & 0xFFFFFFFF),
+         lambda x, y, z: x ^ (y | (~z & 0xFFFFFFFF))]
+    KL = [0x00000000, 0x5A827999, 0x6ED9EBA1, 0x8F1BBCDC, 0xA953FD4E]
+    KR = [0x50A28BE6, 0x5C4DD124, 0x6D703EF3, 0x7A6D76E9, 0x00000000]
+    RL = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 7, 4, 13, 1, 10, 6, 15, 3, 12, 0, 9, 5, 2, 14, 11, 8,
+          3, 10, 14, 4, 9, 15, 8, 1, 2, 7, 0, 6, 13, 11, 5, 12, 1, 9, 11, 10, 0, 8, 12, 4, 13, 3, 7, 15, 14, 5, 6, 2,
+          4, 0, 5, 9, 7, 12, 2, 10, 14, 1, 3, 8, 11, 6, 15, 13]
+    RR = [5, 14, 7, 0, 9, 2, 11, 4, 13, 6, 15, 8, 1, 10, 3, 12, 6, 11, 3, 7, 0, 13, 5, 10, 14, 15, 8, 12, 4, 9, 1, 2,
+          15, 5, 1, 3, 7, 14, 6, 9, 11, 8, 12, 2, 10, 0, 4, 13, 8, 6, 4, 1, 3, 11, 15, 0, 5, 12, 2, 13, 9, 7, 10, 14,
+          12, 15, 10, 4, 1, 5, 8, 7, 6, 2, 13, 14, 0, 3, 9, 11]
+    SL = [11, 14, 15, 12, 5, 8, 7, 9, 11, 13, 14, 15, 6, 7, 9, 8, 7, 6, 8, 13, 11, 9, 7, 15, 7, 12, 15, 9, 11, 7, 13, 12,
+          11, 13, 6, 7, 14, 9, 13, 15, 14, 8, 13, 6, 5, 12, 7, 5, 11, 12, 14, 15, 14, 15, 9, 8, 9, 14, 5, 6, 8, 6, 5, 12,
+          9, 15, 5, 11, 6, 8, 13, 12, 5, 12, 13, 14, 11, 8, 5, 6]
+    SR = [8, 9, 9, 11, 13, 15, 15, 5, 7, 7, 8, 11, 14, 14, 12, 6, 9, 13, 15, 7, 12, 8, 9, 11, 7, 7, 12, 7, 6, 15, 13, 11,
+          9, 7, 15, 11, 8, 6, 6, 14, 12, 13, 5, 14, 13, 13, 7, 5, 15, 5, 8, 11, 14, 14, 6, 14, 6, 9, 12, 9, 12, 5, 15, 8,
+          8, 5, 12, 9, 12, 5, 14, 6, 8, 13, 6, 5, 15, 13, 11, 11]
+    h = [0x67452301, 0xEFCDAB89, 0x98BADCFE, 0x10325476, 0xC3D2E1F0]
+    msg = data + b"\x80" + b"\x00" * ((55 - len(data)) % 64) + struct.pack("<Q", 8 * len(data))
+    for off in range(0, len(msg), 64):
+        X = struct.unpack("<16I", msg[off:off + 64])
+        al, bl, cl, dl, el = h
+        ar, br, cr, dr, er = h
+        for j in range(80):
+            r = j // 16
+            t = (rol((al + f[r](bl, cl, dl) + X[RL[j]] + KL[r]) & 0xFFFFFFFF, SL[j]) + el) & 0xFFFFFFFF
+            al, el, dl, cl, bl = el, dl, rol(cl, 10), bl, t
+            t = (rol((ar + f[4 - r](br, cr, dr) + X[RR[j]] + KR[r]) & 0xFFFFFFFF, SR[j]) + er) & 0xFFFFFFFF
+            ar, er, dr, cr, br = er, dr, rol(cr, 10), br, t
+        t = (h[1] + cl + dr) & 0xFFFFFFFF
+        h[1] = (h[2] + dl + er) & 0xFFFFFFFF
+        h[2] = (h[3] + el + ar) & 0xFFFFFFFF
+        h[3] = (h[4] + al + br) & 0xFFFFFFFF
+        h[4] = (h[0] + bl + cr) & 0xFFFFFFFF
+        h[0] = t
+    return struct.pack("<5I", *h).hex()
+
+
+
 def self_distances(desc_dev):
     """Distance from each descriptor to its nearest *other* descriptor: slot 1 of the exact
     self top-2, as float64 holding float32 values (what `r[1].distance` gives at
@@ -143,7 +191,7 @@ class Metric_Cache(object):
         metric = options.get("metric", "minkowski")
         thumb_x, thumb_y = options.get("thumb_size", (600, 600))
         self.cache_dir = options.get("cache_dir", "data/image_data")
-        if not force_reload and self.load(self.cache_dir):
+        if not force_reload and self.load(self.cache_dir, metric):
             return
         self.create_thumbnail(path, thumb_x, thumb_y)
         self.create_image(path, max_size, metric)
@@ -179,17 +227,6 @@ class Metric_Cache(object):
         self._fill(self.original, descriptors, [k.pt for k in keypoints], (img.shape[1], img.shape[0]))
         self.original["position_tree"] = BallTree(self.original["positions"], metric=metric)
 
-    @staticmethod
-    def _load_tree(data):
-        try:
-            raw = data["position_tree"]
-            raw = raw.tobytes() if raw.dtype == numpy.uint8 else raw.item()
-            tree = pickle.loads(raw)
-            tree.query_radius(numpy.zeros((1, 2)), r=1.0)
-            return tree
-        except Exception:  # noqa: BLE001
-            return BallTree(numpy.asarray(data["positions"], dtype=numpy.float64).reshape(-1, 2), metric="minkowski")
-
     # -- lookups ------------------------------------------------------------------
     def get_indices(self, x, y, radius, options={}):
         """Indices of the features within `radius` px of (x, y), nearest first (the order
@@ -209,40 +246,43 @@ class Metric_Cache(object):
 
     # -- persistence (cache.pyx:191-239) ----------------------------------------------
     def _key(self):
-        try:
-            h = hashlib.new("ripemd160")
-        except ValueError:  # OpenSSL builds without the legacy provider
-            h = hashlib.sha1()
-        h.update(self.path.encode("utf-8") if isinstance(self.path, str) else self.path)
-        return h.hexdigest()
+        return _ripemd160(self.path.encode("utf-8") if isinstance(self.path, str) else self.path)
 
     def save(self, dir="data/image_data"):
+        """Same two files as the reference (<key>.npz, <key>_thumb.npz), with u8 descriptors, the
+        EXACT self-match distances and a flag that says so.  The position tree is not stored: it is
+        rebuilt from the positions on load (milliseconds), so loading never unpickles anything."""
         key = self._key()
         if not os.path.exists(dir):
             os.makedirs(dir)
         o, t = self.original, self.thumb
         numpy.savez("%s/%s" % (dir, key), descriptors=o["descriptors"].cpu().numpy(),
-                    positions=o["positions"], distances=o["distances"],
-                    position_tree=numpy.frombuffer(pickle.dumps(o["position_tree"]), dtype=numpy.uint8),
-                    size=o["size"], exact_self_match=True)
+                    positions=o["positions"], distances=o["distances"], size=o["size"], exact_self_match=True)
         numpy.savez("%s/%s_thumb" % (dir, key), positions=t["positions"],
-                    descriptors=t["descriptors"].cpu().numpy(), distances=t["distances"], size=t["size"])
+                    descriptors=t["descriptors"].cpu().numpy(), distances=t["distances"], size=t["size"],
+                    exact_self_match=True)
         return key
 
-    def load(self, dir="data/image_data"):
+    def load(self, dir="data/image_data", metric="minkowski"):
+        """Reads this class's files and the reference's layout (cache.pyx:200-210: float32
+        integer-valued descriptors, `distances` from the approximate and non-deterministic FLANN
+        self-match, a BallTree pickled into a 0-d object array).  Files without the
+        `exact_self_match` flag get their distances recomputed by the exact CUDA self-match (one
+        top-2 call each), so ratios never mix approximate denominators with exact numerators; the
+        pickled tree is ignored (never unpickled) and rebuilt from the positions."""
         key = self._key()
         full, thumb = "%s/%s.npz" % (dir, key), "%s/%s_thumb.npz" % (dir, key)
         if not (os.path.isfile(full) and os.path.isfile(thumb)):
             return False
-        # also reads the reference's layout (float32 integer-valued descriptors, FLANN distances,
-        # BallTree pickled by an older scikit-learn): descriptors are converted exactly, a tree
-        # that does not unpickle is rebuilt from the positions
-        data, data_thumb = numpy.load(full, allow_pickle=True), numpy.load(thumb, allow_pickle=True)
-        self.thumb = {"positions": data_thumb["positions"],
-                      "descriptors": matchutil.to_device(data_thumb["descriptors"], self.device),
-                      "distances": data_thumb["distances"], "size": tuple(int(v) for v in data_thumb["size"])}
-        self.original = {"descriptors": matchutil.to_device(data["descriptors"], self.device),
-                         "positions": data["positions"], "distances": data["distances"],
-                         "position_tree": self._load_tree(data),
-                         "size": tuple(int(v) for v in data["size"])}
+        slots = []
+        for fname in (thumb, full):
+            with numpy.load(fname, allow_pickle=False) as data:      # object entries are never touched
+                dev = matchutil.to_device(data["descriptors"], self.device)
+                exact = "exact_self_match" in data.files and bool(data["exact_self_match"])
+                slots.append({"positions": numpy.asarray(data["positions"], dtype=numpy.float64).reshape(-1, 2),
+                              "descriptors": dev,
+                              "distances": numpy.asarray(data["distances"], dtype=numpy.float64) if exact else self_distances(dev),
+                              "size": tuple(int(v) for v in data["size"])})
+        self.thumb, self.original = slots
+        self.original["position_tree"] = BallTree(self.original["positions"], metric=metric)
         return True

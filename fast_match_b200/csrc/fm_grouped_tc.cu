@@ -42,6 +42,7 @@ constexpr int COLS_PER_WARP = BN / 2;    // a warp sweeps one column half of a u
 constexpr int A_BYTES = BM * FM_DIM, B_BYTES = BN * FM_DIM, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int BOX_ROWS = 32, BOX_BYTES = BOX_ROWS * FM_DIM;
 constexpr int RING = 8;
+constexpr int NORM_WARPS = 2;            // warps 2 and 3
 constexpr int I32_MAX = 0x7FFFFFFF;
 constexpr int NONE_P = 0x7FFFFF;
 
@@ -49,11 +50,13 @@ enum { F_PASS1 = 1, F_FIRST = 2, F_LAST = 4, F_STOP = 8 };
 
 struct __align__(16) Slot {
     int a_row0, a_valid, b_row0, b_valid, a_out0, b_local0, flags, n_mma;
-    int ck[BN];            // |b_c|^2 * 256 + c for the unit's B rows (INT_MAX beyond b_valid)
+    int ck[BN];            // |b_c|^2 * 256 + c for the unit's B rows (written by the norm warps)
+    int an[BM];            // |a_i|^2 of the unit's A rows (only for the last unit of a slab)
 };
 
 struct __align__(8) Bars {
     unsigned long long full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2];
+    unsigned long long norm_full[2 * RING];   // per ring slot: its ck / an entries are in place
     uint32_t tmem_base, pad;
     int stage_slot[STAGES + 1];     // ring slot of the unit that travels in each TMA stage
 };
@@ -67,7 +70,6 @@ constexpr int SMEM_ALLOC = SMEM_TOTAL + 1024;
 
 struct Params {
     const int64_t *q_off, *t_off, *t_base;   // t_base nullable
-    const int *qnorm, *tnorm;                // per row of the (packed) query rows / target pool
     int32_t G;
     int *counter;
     uint32_t *q2t_d2;
@@ -106,44 +108,39 @@ __device__ __forceinline__ unsigned umin32(const int (&v)[32], int base) {
     return umin3i(umin3i(a, b, c), t[9], t[10]);
 }
 
-// gather + norms in one launch over both pools: rows [0, nq) are query rows (gathered and packed when
-// q_gather is given), rows [nq, nq + nt) target rows.  Also resets the main kernel's group counter.
-__global__ void k_pack_norms(const uint8_t *__restrict__ qpool, const int32_t *__restrict__ gather, int64_t nq,
-                             uint8_t *__restrict__ qpacked, int *__restrict__ qnorms,
-                             const uint8_t *__restrict__ tpool, int64_t nt, int *__restrict__ tnorms,
-                             int *__restrict__ counter) {
+// Queries given by index (q_gather) are packed once so that TMA can fetch a round's rows as
+// contiguous boxes.  16 bytes per thread, four loads in flight.
+__global__ void k_pack(const uint8_t *__restrict__ qpool, const int32_t *__restrict__ gather, int64_t nq,
+                       uint8_t *__restrict__ qpacked) {
     const int64_t gt = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (gt == 0) *counter = 0;
     const int sub = (int)(gt & 7);                // 8 threads (16 B each) per descriptor
-    constexpr int U = 4;                          // descriptors per thread group: 4 loads in flight per thread
-    const int64_t half = (nq + nt + U - 1) / U;   // row r of this group and r + half, r + 2 half, ...
+    constexpr int U = 4;
+    const int64_t quarter = (nq + U - 1) / U;
     uint4 x[U];
-    int64_t row[U];
-    bool is_q[U], live[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-        int64_t r = (gt >> 3) + k * half;
-        live[k] = (gt >> 3) < half && r < nq + nt;
-        is_q[k] = r < nq;
-        if (!is_q[k]) r -= nq;
-        row[k] = r;
+        const int64_t r = (gt >> 3) + k * quarter;
         x[k] = make_uint4(0, 0, 0, 0);
-        if (live[k]) {
-            const int64_t src = (is_q[k] && gather) ? (int64_t)gather[r] : r;
-            x[k] = *(const uint4 *)((is_q[k] ? qpool : tpool) + src * FM_DIM + sub * 16);
-        }
+        if ((gt >> 3) < quarter && r < nq) x[k] = *(const uint4 *)(qpool + (int64_t)gather[r] * FM_DIM + sub * 16);
     }
 #pragma unroll
     for (int k = 0; k < U; ++k) {
-        if (live[k] && is_q[k] && qpacked) *(uint4 *)(qpacked + row[k] * FM_DIM + sub * 16) = x[k];
-        unsigned s = 0;
-        s = __dp4a(x[k].x, x[k].x, s); s = __dp4a(x[k].y, x[k].y, s);
-        s = __dp4a(x[k].z, x[k].z, s); s = __dp4a(x[k].w, x[k].w, s);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (sub == 0 && live[k]) (is_q[k] ? qnorms : tnorms)[row[k]] = (int)s;
+        const int64_t r = (gt >> 3) + k * quarter;
+        if ((gt >> 3) < quarter && r < nq) *(uint4 *)(qpacked + r * FM_DIM + sub * 16) = x[k];
     }
+}
+
+// |row|^2 of one staged descriptor (128 B, 128B-swizzled tile: the swizzle only permutes the 16-byte
+// chunks inside the row, so the sum is taken in whatever order avoids bank conflicts)
+__device__ __forceinline__ int row_norm(uint32_t tile_saddr, int r) {
+    unsigned s = 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int4 x = ld_shared_v4(tile_saddr + r * FM_DIM + ((c ^ (r & 7)) << 4));
+        s = __dp4a((unsigned)x.x, (unsigned)x.x, s); s = __dp4a((unsigned)x.y, (unsigned)x.y, s);
+        s = __dp4a((unsigned)x.z, (unsigned)x.z, s); s = __dp4a((unsigned)x.w, (unsigned)x.w, s);
+    }
+    return (int)s;
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -161,8 +158,10 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 #endif
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1); }
+        // a stage is free again when the MMAs that read it have completed (tcgen05.commit) and both norm warps are done with it
+        for (int i = 0; i < STAGES; ++i) { mbar_init(smem_u32(&bars->full[i]), 1); mbar_init(smem_u32(&bars->empty[i]), 1 + NORM_WARPS); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->tmem_full[i]), 1); mbar_init(smem_u32(&bars->tmem_empty[i]), EPI_WARPS / 2); }
+        for (int i = 0; i < 2 * RING; ++i) mbar_init(smem_u32(&bars->norm_full[i]), NORM_WARPS);
         fence_barrier_init();
         tma_prefetch_desc(&map_q);
         tma_prefetch_desc(&map_t);
@@ -176,95 +175,117 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     if (warp == 0) {
         // ===================== producer: claims groups, emits units =====================
         // All B-chunks of a slab go to the same accumulator buffer (= the same epilogue group, which
-        // carries the rows' running minima across the chunks); consecutive slabs alternate buffers.
-        int u = 0, nslab = 0, nb[2] = {0, 0};
-        bool done = false;
-        while (!done) {
-            int g = 0;
-            if (lane == 0) g = atomicAdd(P.counter, 1);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            const bool stop = g >= P.G;
-            int64_t q0 = 0, t0 = 0, tsrc = 0;
-            int nq = 0, nt = 0;
-            if (!stop) {
-                q0 = P.q_off[g]; nq = (int)(P.q_off[g + 1] - q0);
-                t0 = P.t_off[g]; nt = (int)(P.t_off[g + 1] - t0);
-                tsrc = P.t_base ? P.t_base[g] : t0;
-            }
-            // after the last group: one stop unit per accumulator buffer
-            const int npass = stop ? 2 : ((nq == 0 || nt == 0) ? 0 : 2);
-            for (int pass = 0; pass < npass; ++pass) {
-                const int na = stop ? 1 : (pass == 0 ? nq : nt), nbr = stop ? 1 : (pass == 0 ? nt : nq);
-                const int64_t a_src = pass == 0 ? q0 : tsrc, b_src = pass == 0 ? tsrc : q0;
-                const int64_t a_out = pass == 0 ? q0 : t0;
-                const int *bnorm = pass == 0 ? P.tnorm : P.qnorm;
-                const CUtensorMap *amap = pass == 0 ? &map_q : &map_t, *bmap = pass == 0 ? &map_t : &map_q;
-                for (int a0 = 0; a0 < na; a0 += BM, ++nslab) {
-                    const int buf = stop ? pass : (nslab & 1);
-                    for (int b0 = 0; b0 < nbr; b0 += BN, ++u) {
-                        const int stage = u % STAGES;
-                        const int slot_idx = buf * RING + (nb[buf]++ % RING);
-                        Slot *sl = &ring[slot_idx];
-                        const int a_valid = min(BM, na - a0), b_valid = min(BN, nbr - b0);
-                        // |b_c|^2 of the unit's B rows: independent of the pipeline state, so the
-                        // loads are in flight while the warp waits for a free stage
-                        int bn[BN / 32];
-#pragma unroll
-                        for (int k = 0; k < BN / 32; ++k) {
-                            const int c = lane + 32 * k;
-                            bn[k] = (!stop && c < b_valid) ? __ldg(bnorm + b_src + b0 + c) : -1;
-                        }
-                        GP_T(_p0);
-                        mbar_wait(smem_u32(&bars->empty[stage]), ((u / STAGES) & 1) ^ 1);
-                        GP_T(_p1);
-                        GP_ACC(0, _p0, _p1);
-                        const uint32_t fb = smem_u32(&bars->full[stage]);
-                        if (stop) {
-                            if (lane == 0) {
-                                sl->flags = F_STOP;
-                                bars->stage_slot[stage] = slot_idx;
-                                mbar_expect_tx(fb, 0);
-                            }
-                            __syncwarp();
-                            continue;
-                        }
-                        const int abox = (a_valid + BOX_ROWS - 1) / BOX_ROWS, bbox = (b_valid + BOX_ROWS - 1) / BOX_ROWS;
-                        // exact-key constants of the B rows (all lanes), header + barrier arming (lane 0)
-#pragma unroll
-                        for (int k = 0; k < BN / 32; ++k) {
-                            const int c = lane + 32 * k;
-                            sl->ck[c] = bn[k] >= 0 ? (int)(((unsigned)bn[k] << 8) | (unsigned)c) : I32_MAX;
-                        }
-                        if (lane == 0) {
-                            sl->a_row0 = (int)(a_src + a0); sl->a_valid = a_valid;
-                            sl->b_row0 = (int)(b_src + b0); sl->b_valid = b_valid;
-                            sl->a_out0 = (int)(a_out + a0); sl->b_local0 = b0;
-                            sl->flags = (pass ? F_PASS1 : 0) | (b0 == 0 ? F_FIRST : 0) | (b0 + BN >= nbr ? F_LAST : 0);
-                            sl->n_mma = (b_valid + 15) & ~15;
-                            bars->stage_slot[stage] = slot_idx;
-                        }
-                        __syncwarp();
-                        // 32-row boxes (only the rows the unit needs are read): up to 4 for the A slab,
-                        // up to 8 for the B rows; everything below is warp-uniform, one elected lane issues
-                        const uint32_t sa = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + SMEM_STAGES + stage * STAGE_BYTES;
-                        const int arow = (int)(a_src + a0), brow = (int)(b_src + b0);
-                        if (elect_one()) {
-                            mbar_expect_tx(fb, (abox + bbox) * BOX_BYTES);
-                            for (int i = 0; i < abox; ++i)
-                                tma_load_2d(sa + i * BOX_BYTES, amap, 0, arow + i * BOX_ROWS, fb);
-                            for (int i = 0; i < bbox; ++i)
-                                tma_load_2d(sa + A_BYTES + i * BOX_BYTES, bmap, 0, brow + i * BOX_ROWS, fb);
-                        }
-                        __syncwarp();
-                        GP_T(_p2);
-                        GP_ACC(1, _p1, _p2);
-#ifdef FM_TC_PROF
-                        _gp[2] += 1;
-#endif
+        // carries the rows' running minima across the chunks).  Two slabs are in flight, one per
+        // buffer, and their units are emitted alternately, so that the tensor core fills one
+        // accumulator while the other group drains its own (the MMAs are issued in unit order: two
+        // consecutive units on the same buffer would serialise MMA and epilogue).
+        // Groups are claimed two steps ahead (atomic, then offsets) so that neither latency is exposed.
+        struct Stream { bool active; int pass, na, nbr, a0, b0; int64_t a_src, b_src, a_out; };
+        Stream st[2];
+        st[0].active = st[1].active = false;
+        bool stopped[2] = {false, false};
+        // claim pipeline
+        int claimed = lane == 0 ? atomicAdd(P.counter, 1) : 0;                 // stage 1: atomic in flight
+        int g1 = __shfl_sync(0xffffffffu, claimed, 0);                         // stage 2: offsets in flight
+        int64_t o1_q0 = 0, o1_q1 = 0, o1_t0 = 0, o1_t1 = 0, o1_tb = 0;
+        if (g1 < P.G) {
+            o1_q0 = P.q_off[g1]; o1_q1 = P.q_off[g1 + 1]; o1_t0 = P.t_off[g1]; o1_t1 = P.t_off[g1 + 1];
+            o1_tb = P.t_base ? P.t_base[g1] : o1_t0;
+        }
+        claimed = lane == 0 ? atomicAdd(P.counter, 1) : 0;
+        // current group / slab iterator
+        bool have_group = false, exhausted = false;
+        int64_t q0 = 0, t0 = 0, tsrc = 0;
+        int nq = 0, nt = 0, it_pass = 0, it_a0 = 0;
+        int u = 0, nb[2] = {0, 0};
+
+        auto next_slab = [&](Stream &x) -> bool {
+            for (;;) {
+                if (!have_group) {
+                    if (g1 >= P.G) { exhausted = true; return false; }
+                    q0 = o1_q0; nq = (int)(o1_q1 - o1_q0); t0 = o1_t0; nt = (int)(o1_t1 - o1_t0); tsrc = o1_tb;
+                    g1 = __shfl_sync(0xffffffffu, claimed, 0);
+                    if (g1 < P.G) {
+                        o1_q0 = P.q_off[g1]; o1_q1 = P.q_off[g1 + 1]; o1_t0 = P.t_off[g1]; o1_t1 = P.t_off[g1 + 1];
+                        o1_tb = P.t_base ? P.t_base[g1] : o1_t0;
                     }
+                    claimed = lane == 0 ? atomicAdd(P.counter, 1) : 0;
+                    if (nq == 0 || nt == 0) continue;          // nothing to multiply (k_mutual fills these rows)
+                    have_group = true; it_pass = 0; it_a0 = 0;
                 }
+                const int na = it_pass == 0 ? nq : nt;
+                if (it_a0 >= na) {
+                    if (it_pass == 0) { it_pass = 1; it_a0 = 0; } else have_group = false;
+                    continue;
+                }
+                x.active = true; x.pass = it_pass; x.na = na; x.nbr = it_pass == 0 ? nt : nq;
+                x.a0 = it_a0; x.b0 = 0;
+                x.a_src = it_pass == 0 ? q0 : tsrc; x.b_src = it_pass == 0 ? tsrc : q0;
+                x.a_out = it_pass == 0 ? q0 : t0;
+                it_a0 += BM;
+                return true;
             }
-            if (stop) done = true;
+        };
+
+        while (!(stopped[0] && stopped[1])) {
+#pragma unroll
+            for (int buf = 0; buf < 2; ++buf) {
+                if (stopped[buf]) continue;
+                Stream &x = st[buf];
+                bool stop = false;
+                if (!x.active && (exhausted || !next_slab(x))) stop = true;
+                const int stage = u % STAGES;
+                const int slot_idx = buf * RING + (nb[buf]++ % RING);
+                Slot *sl = &ring[slot_idx];
+                GP_T(_p0);
+                mbar_wait(smem_u32(&bars->empty[stage]), ((u / STAGES) & 1) ^ 1);
+                GP_T(_p1);
+                GP_ACC(0, _p0, _p1);
+                const uint32_t fb = smem_u32(&bars->full[stage]);
+                ++u;
+                if (stop) {                 // after the last slab: one stop unit per accumulator buffer
+                    if (lane == 0) {
+                        sl->flags = F_STOP;
+                        bars->stage_slot[stage] = slot_idx;
+                        mbar_expect_tx(fb, 0);
+                    }
+                    __syncwarp();
+                    stopped[buf] = true;
+                    continue;
+                }
+                const int a_valid = min(BM, x.na - x.a0), b_valid = min(BN, x.nbr - x.b0);
+                const int abox = (a_valid + BOX_ROWS - 1) / BOX_ROWS, bbox = (b_valid + BOX_ROWS - 1) / BOX_ROWS;
+                const int arow = (int)(x.a_src + x.a0), brow = (int)(x.b_src + x.b0);
+                // unit header (the norm warps fill in ck / an once the tiles have landed)
+                if (lane == 0) {
+                    sl->a_row0 = arow; sl->a_valid = a_valid;
+                    sl->b_row0 = brow; sl->b_valid = b_valid;
+                    sl->a_out0 = (int)(x.a_out + x.a0); sl->b_local0 = x.b0;
+                    sl->flags = (x.pass ? F_PASS1 : 0) | (x.b0 == 0 ? F_FIRST : 0) | (x.b0 + BN >= x.nbr ? F_LAST : 0);
+                    sl->n_mma = (b_valid + 15) & ~15;
+                    bars->stage_slot[stage] = slot_idx;
+                }
+                __syncwarp();
+                // 32-row boxes (only the rows the unit needs are read): up to 4 for the A slab,
+                // up to 8 for the B rows; everything below is warp-uniform, one elected lane issues
+                const uint32_t sa = __shfl_sync(0xffffffffu, smem_u32(smem), 0) + SMEM_STAGES + stage * STAGE_BYTES;
+                const CUtensorMap *amap = x.pass == 0 ? &map_q : &map_t, *bmap = x.pass == 0 ? &map_t : &map_q;
+                if (elect_one()) {
+                    mbar_expect_tx(fb, (abox + bbox) * BOX_BYTES);
+                    for (int i = 0; i < abox; ++i)
+                        tma_load_2d(sa + i * BOX_BYTES, amap, 0, arow + i * BOX_ROWS, fb);
+                    for (int i = 0; i < bbox; ++i)
+                        tma_load_2d(sa + A_BYTES + i * BOX_BYTES, bmap, 0, brow + i * BOX_ROWS, fb);
+                }
+                __syncwarp();
+                x.b0 += BN;
+                if (x.b0 >= x.nbr) x.active = false;
+                GP_T(_p2);
+                GP_ACC(1, _p1, _p2);
+#ifdef FM_TC_PROF
+                _gp[2] += 1;
+#endif
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
@@ -319,6 +340,37 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 GP_ACC(5, _m2, _m3);
             }
         }
+    } else if (warp == 2 || warp == 3) {
+        // ===================== norm warps =====================
+        // |b_c|^2 of every B row (-> exact-key constants) and, for the last unit of a slab, |a_i|^2 of
+        // the A rows, summed from the staged tiles while the tensor core multiplies them.
+        const int t64 = (warp - 2) * 32 + lane;
+        const uint32_t sbase = smem_u32(smem);
+        int stops = 0;
+        for (int u = 0; stops < 2; ++u) {
+            const int stage = u % STAGES;
+            mbar_wait(smem_u32(&bars->full[stage]), (u / STAGES) & 1);
+            const int slot_idx = bars->stage_slot[stage];
+            Slot *sl = &ring[slot_idx];
+            const int flags = sl->flags;
+            if (!(flags & F_STOP)) {
+                const uint32_t sa = sbase + SMEM_STAGES + stage * STAGE_BYTES;
+                const int b_valid = sl->b_valid;
+                for (int r = t64; r < b_valid; r += NORM_WARPS * 32)
+                    sl->ck[r] = (int)(((unsigned)row_norm(sa + A_BYTES, r) << 8) | (unsigned)r);
+                if (flags & F_LAST) {
+                    const int a_valid = sl->a_valid;
+                    for (int r = t64; r < a_valid; r += NORM_WARPS * 32) sl->an[r] = row_norm(sa, r);
+                }
+            } else {
+                ++stops;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&bars->norm_full[slot_idx]));
+                mbar_arrive(smem_u32(&bars->empty[stage]));
+            }
+        }
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         // Two groups of 8 warps, one per accumulator buffer; a warp owns 32 rows (its TMEM lane
@@ -335,18 +387,20 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             GP_ACC(6, _e0, _e1);
             tc_fence_after();
             const Slot *sl = &ring[grp * RING + (k % RING)];
+            mbar_wait(smem_u32(&bars->norm_full[grp * RING + (k % RING)]), (k / RING) & 1);
             const int flags = sl->flags;
             if (flags & F_STOP) break;
             const int b_valid = sl->b_valid, b_local0 = sl->b_local0;
             // the unit's valid columns are split evenly (in 32-column pieces) between the two warps
             // that sweep a row, so that short units do not leave the second one idle
             const int half = ((b_valid + 63) >> 6) << 5;                                   // <= 128
-            const int ncols = ch ? max(b_valid - half, 0) : min(half, b_valid);            // warp-uniform
+            // (a warp whose 32 rows all lie beyond the slab's last valid row has nothing to sweep)
+            const int ncols = lq * 32 >= sl->a_valid ? 0 : (ch ? max(b_valid - half, 0) : min(half, b_valid));   // warp-uniform
             const uint32_t taddr0 = taddr_grp + ch * half;
             const bool top1 = (flags & F_PASS1) != 0;                                      // warp-uniform
-            // |a_i|^2 is only needed when the slab is written out: issue the load now, use it last
+            // |a_i|^2 is only needed when the slab is written out
             int an = 0;
-            if ((flags & F_LAST) && row < sl->a_valid) an = __ldg((top1 ? P.tnorm : P.qnorm) + sl->a_row0 + row);
+            if ((flags & F_LAST) && row < sl->a_valid) an = sl->an[row];
             if (flags & F_FIRST) { m1 = m2 = NONE_P; i1 = i2 = -1; }
             const uint32_t cka = smem_u32(&sl->ck[0]) + ch * half * 4;
             int k1 = I32_MAX, k2 = I32_MAX;
@@ -510,8 +564,8 @@ extern "C" int fm_debug_gprof(unsigned long long *out16, int reset) {
 
 size_t grouped_tc_workspace_bytes(int64_t total_q, int64_t tpool_rows, bool gather) {
     using namespace gtc;
-    return up256(256) + up256((size_t)(total_q + 8) * 4) + up256((size_t)(tpool_rows + 8) * 4) +
-           (gather ? up256((size_t)total_q * FM_DIM) : 0) + 256;
+    (void)tpool_rows;
+    return up256(256) + (gather ? up256((size_t)total_q * FM_DIM) : 0) + 256;
 }
 
 int launch_grouped_tc(const uint8_t *qpool, const int32_t *q_gather, const int64_t *q_off,
@@ -536,13 +590,13 @@ int launch_grouped_tc(const uint8_t *qpool, const int32_t *q_gather, const int64
     {
         uint8_t *w = (uint8_t *)ws;
         int *counter = (int *)w; w += up256(256);
-        int *qnorm = (int *)w; w += up256((size_t)(total_q + 8) * 4);
-        int *tnorm = (int *)w; w += up256((size_t)(tpool_rows + 8) * 4);
         uint8_t *qpack = q_gather ? w : nullptr;
-        k_pack_norms<<<(unsigned)((((total_q + tpool_rows + 3) / 4) * 8 + 255) / 256), 256, 0, s>>>(
-            qpool, q_gather, total_q, qpack, qnorm, tpool, tpool_rows, tnorm, counter);
-        FM_CUDA_TRY(cudaGetLastError());
-        count_launch();
+        FM_CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(int), s));          // the kernel's group counter
+        if (q_gather) {
+            k_pack<<<(unsigned)((((total_q + 3) / 4) * 8 + 255) / 256), 256, 0, s>>>(qpool, q_gather, total_q, qpack);
+            FM_CUDA_TRY(cudaGetLastError());
+            count_launch();
+        }
         CUtensorMap map_q, map_t;
         int rc;
         if ((rc = make_map(&map_q, qpack ? qpack : qpool, total_q, FM_DIM, BOX_ROWS, CU_TENSOR_MAP_SWIZZLE_128B)) != FM_OK) return rc;
@@ -563,7 +617,7 @@ int launch_grouped_tc(const uint8_t *qpool, const int32_t *q_gather, const int64
             }
             if (sm_count[slot] > 0) sms = sm_count[slot];
         }
-        Params P{q_off, t_off, t_base, qnorm, tnorm, G, counter, q2t_d2, q2t_idx, t2q_idx};
+        Params P{q_off, t_off, t_base, G, counter, q2t_d2, q2t_idx, t2q_idx};
         const int grid = G < sms ? G : sms;
         prof_begin(s);
         k_grouped_tc<<<grid, NTHREADS, SMEM_ALLOC, s>>>(map_q, map_t, P);

@@ -41,6 +41,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     unsigned long long t0 = 0;
     uint32_t spins = 0;
     while (!mbar_try(bar, parity)) {
+#ifdef FM_SPIN_SLEEP
+        __nanosleep(FM_SPIN_SLEEP);     // leave the issue slots to the warps that have work
+#endif
         if ((++spins & 0xFFF) == 0) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));

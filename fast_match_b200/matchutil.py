@@ -123,7 +123,13 @@ def _knn(dt1, dt2, k, cross_check, device=None):
 
 
 def bf_match(dt1, dt2, k=1, options={}):
-    """Exact k-NN (k <= 2) under L2; crossCheck honoured only when k == 1 (matchutil.py:39-43)."""
+    """Exact k-NN under L2; crossCheck honoured only when k == 1 (matchutil.py:39-43).
+
+    Same arguments as the reference wrapper, narrower domain: the CUDA matcher is a u8 top-2
+    kernel, so descriptors must be 128-d with integer values 0..255 (SIFT as OpenCV emits it; float32
+    arrays holding such values are converted exactly) and k must be 1 or 2.  Anything else --
+    RootSIFT / normalised SIFT, SURF, ORB, k > 2 -- raises ValueError instead of being rounded or
+    silently routed to a CPU matcher; keep cv2.BFMatcher for those."""
     cross_check = k == 1 and options.get("crossCheck", False) == True  # noqa: E712
     return _knn(dt1, dt2, k, cross_check, options.get("device"))
 
@@ -131,5 +137,7 @@ def bf_match(dt1, dt2, k=1, options={}):
 def flann_match(dt1, dt2, k=1, options={}):
     """Same signature as the reference's FLANN wrapper (matchutil.py:46-67).  The kd-forest
     parameters (algorithm / trees / checks) are accepted and ignored: the exact kernel is
-    faster than the approximate index it replaces, so the result is the exact k-NN."""
+    faster than the approximate index it replaces, so the result is the exact k-NN (FLANN's own
+    answers differ from it on 3-15 % of the rows: see bench.py's flann_recall leg).  Same domain
+    restriction as bf_match (128-d integer-valued 0..255 descriptors, k <= 2)."""
     return _knn(dt1, dt2, k, False, options.get("device"))

@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+import frozen
 import oracle
 from oracle import fastmatch_ref
 from fast_match_b200 import backend, cache as fm_cache, fastmatch, matchutil, sharded, synth
@@ -58,21 +59,76 @@ def test_metric_cache_self_distances_and_get(cuda, tmp_path):
     assert np.array_equal(mc2.get_indices(400, 300, 100), idx)
 
 
+def test_metric_cache_reads_the_reference_layout(cuda, tmp_path):
+    """A cache directory written by the reference (cache.pyx:200-210): float32 integer-valued
+    descriptors, FLANN (approximate) self-match distances, the BallTree pickled into a 0-d object
+    array, file names RIPEMD-160(path).  It must load without unpickling anything, with the
+    distances replaced by the exact self-match."""
+    import pickle
+    from sklearn.neighbors import BallTree
+    path = "some/dir/img4.ppm"
+    key = fm_cache._ripemd160(path.encode("utf-8"))
+    desc, pos = G["graf4_desc"], G["graf4_pos"].astype(np.float64)
+    thumb_desc, thumb_pos = desc[:700], pos[:700] * 0.5
+    od2, _ = oracle.c_top2(desc, desc)
+    exact = np.sqrt(od2[:, 1].astype(np.float32)).astype(np.float64)
+    approx = exact * 1.07                                            # what an approximate index may have stored
+    tree = np.array(pickle.dumps(BallTree(pos, metric="minkowski")), dtype=object)   # 0-d object array, as numpy.savez stores it
+    np.savez(str(tmp_path / key), descriptors=desc.astype(np.float32), positions=pos, distances=approx,
+             position_tree=tree, size=(800, 640))
+    np.savez(str(tmp_path / (key + "_thumb")), positions=thumb_pos, descriptors=thumb_desc.astype(np.float32),
+             distances=np.ones(700), size=(600, 480))
+    mc = fm_cache.Metric_Cache(path, {"cache_dir": str(tmp_path)})      # would try to open the image if load() failed
+    assert mc.original["descriptors"].dtype == torch.uint8 and np.array_equal(mc.original["descriptors"].cpu().numpy(), desc)
+    assert np.array_equal(mc.original["distances"], exact)              # recomputed, not the stored approximation
+    td2, _ = oracle.c_top2(thumb_desc, thumb_desc)
+    assert np.array_equal(mc.thumb["distances"], np.sqrt(td2[:, 1].astype(np.float32)).astype(np.float64))
+    assert mc.original["size"] == (800, 640) and mc.thumb["size"] == (600, 480)
+    idx = mc.get_indices(400, 300, 100)
+    d = np.linalg.norm(pos[idx] - np.array([400, 300]), axis=1)
+    assert len(idx) > 0 and (d <= 100).all() and (np.diff(d) >= 0).all()
+    # files written by this class carry the flag and are trusted as they are
+    mc.save(str(tmp_path / "new"))
+    mc2 = fm_cache.Metric_Cache(path, {"cache_dir": str(tmp_path / "new")})
+    assert np.array_equal(mc2.original["distances"], exact) and torch.equal(mc2.thumb["descriptors"], mc.thumb["descriptors"])
+
+
+def test_two_devices_in_one_process(cuda):
+    """Per-device state of the library (shared-memory opt-in, SM count, cluster support, host-path
+    context): the second GPU of a process must behave like the first."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    q, t = synth.make_pair(3000, 2500, seed=42)
+    od2, oidx = oracle.c_top2(q, t)
+    qpool, q_off, tpool, t_off = synth.make_groups(40, 16, 200, seed=7)
+    gd2, gidx, gt2q = oracle.c_grouped_mutual(qpool, q_off, tpool, t_off)
+    for dev in ("cuda:1", "cuda:0", "cuda:1"):
+        d = torch.device(dev)
+        d2, idx = backend.top2(torch.from_numpy(q).to(d), torch.from_numpy(t).to(d), algo=backend.FM_ALGO_TCGEN05)
+        assert np.array_equal(d2.cpu().numpy().view(np.uint32), od2) and np.array_equal(idx.cpu().numpy(), oidx)
+        g = backend.grouped_mutual(torch.from_numpy(qpool).to(d), torch.from_numpy(q_off).to(d),
+                                   torch.from_numpy(tpool).to(d), torch.from_numpy(t_off).to(d))
+        assert np.array_equal(g[0].cpu().numpy().view(np.uint32), gd2) and np.array_equal(g[2].cpu().numpy(), gt2q)
+        before = torch.cuda.current_device()
+        hd2, hidx, _ = backend.top2_host(q, t, device=d.index, want_dist=False)
+        assert torch.cuda.current_device() == before                     # the caller's device is restored
+        assert np.array_equal(hd2, od2) and np.array_equal(hidx, oidx)
+
+
 @pytest.mark.parametrize("opts", [{}, {"grid_size": (75, 75), "grid_margin": 30, "radius": 50}])
 def test_fastmatch_cuda_equals_sequential_oracle(cuda, opts):
     """Config 1 (README example): fastmatch.match on graf img4 -> img1 with the CUDA backend
     (wave-batched grouped launches) == the sequential driver with the integer oracle."""
-    import cv2
-    img1 = cv2.imread(os.path.join(GOLD, "graf1.png"))
-    ref_cache = fastmatch_ref.RefMetricCache.from_image(os.path.join(GOLD, "graf4.png"))
+    img1 = frozen.target_image()
+    ref_cache = frozen.query_cache()             # frozen SIFT features: independent of this box's OpenCV
     o, th = ref_cache.original, ref_cache.thumb
     mc = fm_cache.Metric_Cache.from_features(th["descriptors"], th["positions"], th["size"],
                                              o["descriptors"], o["positions"], o["size"])
     assert np.array_equal(mc.original["distances"], o["distances"])
     for tau in (0.7, 0.9):
         log_a, log_b, stats = [], [], {}
-        got = fastmatch.match(mc, img1, dict(opts, log=log_a, stats=stats))(tau)
-        ref = fastmatch_ref.match(ref_cache, img1, dict(opts, log=log_b))
+        got = fastmatch.match(mc, img1, dict(opts, log=log_a, stats=stats, features=frozen.features))(tau)
+        ref = fastmatch_ref.match(ref_cache, img1, dict(opts, log=log_b, features=frozen.features))
         want = ref(tau)
         assert len(got) == len(want) and len(got) > 0
         for (ia, da), (ib, db) in zip(got, want):
@@ -84,10 +140,13 @@ def test_fastmatch_cuda_equals_sequential_oracle(cuda, opts):
         assert stats["launches"] < ref.rounds
     gold = np.load(os.path.join(GOLD, "fastmatch_graf41.npz"))
     h = gold["query_desc_hash"]
-    if not opts and (int(o["descriptors"].astype(np.uint64).sum()), len(o["descriptors"])) == (int(h[0]), int(h[1])):
-        ms = fastmatch.match(mc, img1, {})(0.7)
-        assert np.array_equal(np.array([m[0] for m in ms], np.int64), gold["tau70_index"])
-        assert np.array_equal(np.array([m[1]["ratio"] for m in ms]), gold["tau70_ratio"])
+    assert (int(o["descriptors"].astype(np.uint64).sum()), len(o["descriptors"])) == (int(h[0]), int(h[1]))
+    if not opts:     # the frozen run with cv2.BFMatcher as the matcher (tests/golden/make_golden.py)
+        for tau, key in ((0.7, "tau70"), (0.9, "tau90")):
+            ms = fastmatch.match(mc, img1, {"features": frozen.features})(tau)
+            assert np.array_equal(np.array([m[0] for m in ms], np.int64), gold[key + "_index"])
+            assert np.array_equal(np.array([m[1]["positions"] for m in ms]).reshape(-1, 2, 2), gold[key + "_pos"])
+            assert np.array_equal(np.array([m[1]["ratio"] for m in ms]), gold[key + "_ratio"])
 
 
 def test_target_sharding_on_one_device_equals_unsharded(cuda):

@@ -11,6 +11,7 @@ import os
 import numpy as np
 import pytest
 
+import frozen
 import oracle
 from oracle import fastmatch_ref
 from fast_match_b200 import cache as fm_cache
@@ -84,10 +85,8 @@ def _same_logs(la, lb):
 
 @pytest.fixture(scope="module")
 def graf():
-    import cv2
-    img1 = cv2.imread(os.path.join(GOLD, "graf1.png"))
-    cache = fastmatch_ref.RefMetricCache.from_image(os.path.join(GOLD, "graf4.png"))
-    return cache, img1
+    """Query cache and target image of the README example, built from the FROZEN features."""
+    return frozen.query_cache(), frozen.target_image()
 
 
 @pytest.mark.parametrize("opts", [{}, {"grid_size": (75, 75), "grid_margin": 30, "radius": 50},
@@ -97,8 +96,8 @@ def test_wave_batched_flood_fill_equals_sequential(monkeypatch, graf, opts):
     _stub_backend(monkeypatch)
     for tau in (0.7, 0.9):
         log_a, log_b, stats = [], [], {}
-        got = fastmatch.match(cache, img1, dict(opts, log=log_a, stats=stats))(tau)
-        ref = fastmatch_ref.match(cache, img1, dict(opts, log=log_b))
+        got = fastmatch.match(cache, img1, dict(opts, log=log_a, stats=stats, features=frozen.features))(tau)
+        ref = fastmatch_ref.match(cache, img1, dict(opts, log=log_b, features=frozen.features))
         want = ref(tau)
         _same_matches(got, want)
         _same_logs(log_a, log_b)
@@ -108,17 +107,18 @@ def test_wave_batched_flood_fill_equals_sequential(monkeypatch, graf, opts):
 
 def test_readme_example_against_frozen_cv2_run(monkeypatch, graf):
     """Config 1: Fast-Match graf img4 -> img1 at tau 0.7 / 0.9 equals the frozen run that used
-    cv2.BFMatcher as the matcher (valid when this box's SIFT reproduces the frozen descriptors)."""
+    cv2.BFMatcher as the matcher.  The inputs are the frozen features (tests/frozen.py), so the test
+    does not depend on this machine's SIFT and never skips."""
     cache, img1 = graf
     gold = np.load(os.path.join(GOLD, "fastmatch_graf41.npz"))
     h = gold["query_desc_hash"]
-    if (int(cache.original["descriptors"].astype(np.uint64).sum()), len(cache.original["descriptors"])) != (int(h[0]), int(h[1])):
-        pytest.skip("cv2 SIFT on this machine does not reproduce the frozen descriptors")
+    assert (int(cache.original["descriptors"].astype(np.uint64).sum()), len(cache.original["descriptors"]),
+            int(cache.thumb["descriptors"].astype(np.uint64).sum())) == (int(h[0]), int(h[1]), int(h[2]))
     _stub_backend(monkeypatch)
     for tau in (0.7, 0.9):
         key = "tau%02d" % int(tau * 100)
         log = []
-        ms = fastmatch.match(cache, img1, {"log": log})(tau)
+        ms = fastmatch.match(cache, img1, {"log": log, "features": frozen.features})(tau)
         assert np.array_equal(np.array([m[0] for m in ms], np.int64), gold[key + "_index"])
         assert np.array_equal(np.array([m[1]["positions"] for m in ms]).reshape(-1, 2, 2), gold[key + "_pos"])
         assert np.array_equal(np.array([m[1]["ratio"] for m in ms]), gold[key + "_ratio"])
@@ -138,6 +138,28 @@ def test_matchlist_behaves_like_knnmatch_output():
     with pytest.raises(ValueError):
         matchutil.to_u8(np.full((2, 128), 0.5, np.float32))       # not integer valued: rejected, not rounded
     assert matchutil.to_u8(None).shape == (0, 128)
+
+
+def test_cache_key_is_ripemd160_with_or_without_openssl_support(monkeypatch):
+    """The reference names cache files RIPEMD-160(path) (cache.pyx:193): the pure-Python fallback
+    must give the same digests as OpenSSL's."""
+    import hashlib
+    vectors = {b"": "9c1185a5c5e9fc54612808977ee8f548b2258d31", b"abc": "8eb208f7e05d987a9b044a8e98c6b087f15a0bfc",
+               b"message digest": "5d0689ef49d2fae572b881b123a85ffa21595f36",
+               b"a" * 1000000: "52783243c1697bdbe16d37f97f68f08325dc1528"}
+    real_new = hashlib.new
+
+    def no_ripemd(name, *a, **k):
+        if name == "ripemd160":
+            raise ValueError("unsupported hash type ripemd160")
+        return real_new(name, *a, **k)
+    monkeypatch.setattr(hashlib, "new", no_ripemd)
+    for msg, want in list(vectors.items())[:3]:
+        assert fm_cache._ripemd160(msg) == want
+    assert fm_cache._ripemd160(b"a" * 10000) == "eb33e86b2400cc0a11707be717a35a9acf074a58"
+    mc = fm_cache.Metric_Cache.__new__(fm_cache.Metric_Cache)
+    mc.path = "data/img4.ppm"
+    assert mc._key() == fm_cache._ripemd160(b"data/img4.ppm") and len(mc._key()) == 40
 
 
 def test_no_cpu_fallback_without_cuda():

@@ -8,8 +8,8 @@ import torch, bench
 from fast_match_b200 import backend
 class A: groups = 10000
 L = backend.lib(); out = (ctypes.c_ulonglong * 16)()
-bench.grouped_leg(A, torch.device("cuda:0"), {}, backend); L.fm_debug_gprof(out, 1)
-a = bench.grouped_leg(A, torch.device("cuda:0"), {}, backend); L.fm_debug_gprof(out, 1)
+bench.grouped_leg(A, torch.device("cuda:0"), {}, backend, False); L.fm_debug_gprof(out, 1)
+a = bench.grouped_leg(A, torch.device("cuda:0"), {}, backend, False); L.fm_debug_gprof(out, 1)
 v = list(out); calls = 8  # 3 warm + 5 timed
 ctas = v[12]; units = v[2]; eu = v[10]
 print("ms", a["ms"], "ctas", ctas, "units(all calls)", units, "cycles/cta/call", v[11] / ctas)

@@ -3,4 +3,4 @@ sys.path.insert(0, ".")
 import bench
 from fast_match_b200 import backend
 class A: groups = 10000
-print(bench.grouped_leg(A, torch.device("cuda:0"), {}, backend)["ms"])
+print(bench.grouped_leg(A, torch.device("cuda:0"), {}, backend, False)["ms"])

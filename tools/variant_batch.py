@@ -7,7 +7,7 @@ from fast_match_b200 import build
 d = os.path.dirname(build.LIB)
 if sys.argv[1] == "build":
     for spec in sys.argv[2:]:
-        name, defs = spec.split("=")
+        name, defs = spec.split("=", 1)
         build.build(defines=[x for x in defs.split(",") if x], out=os.path.join(d, "libfmatch_v_%s.so" % name))
         print("built", name)
 else:
