@@ -237,6 +237,16 @@ class Metric_Cache(object):
                                     sort_results=options.get("sort_results", True))[0]
         return indices[0]
 
+    def get_indices_many(self, points, radius, options={}):
+        """get_indices for many (x, y) at once: one tree query for a whole wave of rounds (the
+        per-call validation of scikit-learn costs more than the search itself)."""
+        if len(points) == 0:
+            return []
+        tree = self.original["position_tree"]
+        ind, _ = tree.query_radius(numpy.asarray(points, dtype=numpy.float64).reshape(-1, 2), r=radius,
+                                   return_distance=True, sort_results=options.get("sort_results", True))
+        return list(ind)
+
     def get(self, x, y, radius, options={}):
         """(descriptors[idx], positions[idx], distances[idx], idx) -- cache.pyx:173-188."""
         idx = self.get_indices(x, y, radius, options)

@@ -149,6 +149,37 @@ def test_fastmatch_cuda_equals_sequential_oracle(cuda, opts):
             assert np.array_equal(np.array([m[1]["ratio"] for m in ms]), gold[key + "_ratio"])
 
 
+def test_match_many_on_cuda_equals_single_pairs(cuda):
+    """fastmatch.match_many: three pairs (two cache objects) through shared grouped launches ==
+    the single-pair driver == the sequential oracle driver."""
+    img1 = frozen.target_image()
+    ref_cache = frozen.query_cache()
+    o, th = ref_cache.original, ref_cache.thumb
+    mk = lambda: fm_cache.Metric_Cache.from_features(th["descriptors"], th["positions"], th["size"],
+                                                     o["descriptors"], o["positions"], o["size"])
+    a, b = mk(), mk()
+    assert hasattr(a, "get_indices_many")
+    pts = [(400, 300), (10, 10), (640, 500)]
+    for got, (x, y) in zip(a.get_indices_many(pts, 100), pts):
+        assert np.array_equal(got, a.get_indices(x, y, 100))
+    for tau in (0.7, 0.9):
+        stats = {}
+        many = fastmatch.match_many([a, b, a], [img1, img1, img1], {"features": frozen.features, "stats": stats})(tau)
+        want = fastmatch_ref.match(ref_cache, img1, {"features": frozen.features})(tau)
+        for ms in many:
+            assert len(ms) == len(want) > 0
+            for (ia, da), (ib, db) in zip(ms, want):
+                assert int(ia) == int(ib) and np.array_equal(da["positions"], db["positions"]) and da["ratio"] == db["ratio"]
+        assert stats["rounds_evaluated"] >= 10 * stats["launches"]
+    # a second tau on the same closure reuses the memoised rounds and the resident pools
+    stats = {}
+    gm = fastmatch.match(a, img1, {"features": frozen.features, "stats": stats})
+    first = gm(0.9)
+    evaluated = stats["rounds_evaluated"]
+    again = gm(0.9)
+    assert stats["rounds_evaluated"] == evaluated and len(again) == len(first)
+
+
 def test_target_sharding_on_one_device_equals_unsharded(cuda):
     """Config 5 at reduced size: S shards processed with t_index_base + merge == one launch."""
     q, t = synth.make_pair(20000, 30001, seed=1239)

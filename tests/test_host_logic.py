@@ -105,6 +105,39 @@ def test_wave_batched_flood_fill_equals_sequential(monkeypatch, graf, opts):
         assert stats["rounds_evaluated"] >= ref.rounds
 
 
+def test_match_many_equals_one_pair_at_a_time(monkeypatch, graf):
+    """Several image pairs in lock step (their waves share the grouped launches, the query caches
+    share one descriptor pool): every pair's matches and log equal a single-pair run."""
+    cache, img1 = graf
+    other = frozen.query_cache()                     # a second cache object: its rows get a non-zero pool base
+    _stub_backend(monkeypatch)
+    for tau in (0.7, 0.9):
+        logs = [[], [], []]
+        stats = {}
+        many = fastmatch.match_many([cache, other, cache], [img1, img1, img1],
+                                    {"log": logs, "features": frozen.features, "stats": stats})(tau)
+        log_one = []
+        one = fastmatch.match(cache, img1, {"log": log_one, "features": frozen.features})(tau)
+        assert len(many) == 3
+        for ms, lg in zip(many, logs):
+            _same_matches(ms, one)
+            _same_logs(lg, log_one)
+    with pytest.raises(ValueError):
+        fastmatch.match_many([cache], [img1, img1])
+
+
+def test_speculation_batches_many_rounds_per_launch(monkeypatch, graf):
+    cache, img1 = graf
+    _stub_backend(monkeypatch)
+    stats = {}
+    ms = fastmatch.match(cache, img1, {"stats": stats, "features": frozen.features})(0.9)
+    ref = fastmatch_ref.match(cache, img1, {"features": frozen.features})
+    ref(0.9)
+    assert len(ms) > 0 and stats["rounds_evaluated"] >= ref.rounds
+    assert stats["rounds_evaluated"] >= 10 * stats["launches"]            # >= 10 rounds per grouped launch
+    assert stats["rounds_evaluated"] <= 1.5 * ref.rounds                  # bounded speculation waste
+
+
 def test_readme_example_against_frozen_cv2_run(monkeypatch, graf):
     """Config 1: Fast-Match graf img4 -> img1 at tau 0.7 / 0.9 equals the frozen run that used
     cv2.BFMatcher as the matcher.  The inputs are the frozen features (tests/frozen.py), so the test
