@@ -192,8 +192,12 @@ static int top2_impl(const uint8_t *q, int64_t M, const uint8_t *t, int64_t N, i
     } else if (algo == FM_ALGO_MMA_SYNC) {
         use_tc = false;
     } else if (algo == FM_ALGO_AUTO) {
-        // the tensor-core kernel pays a fixed set-up cost; tiny problems stay on the warp-MMA path
-        use_tc = fm::tc_supported() && N >= 256 && M * N >= (int64_t)1 << 20;
+        // Measured (tools/quick_perf.py, round 2): with its three launches chained by programmatic
+        // dependent launch the tensor-core path is at least as fast as the warp-MMA kernel from
+        // 300 x 300 up (13 vs 15 us; 2426 x 1058, the README example's thumbnail shape: 17 vs 37 us;
+        // 3668 x 3668, its Metric_Cache self-match: 26 vs 107 us).  Only really tiny problems, where
+        // one launch beats three, stay on the warp-MMA kernel.
+        use_tc = fm::tc_supported() && M * N >= (int64_t)1 << 16;
     } else {
         set_error("%s: unknown algo %d", who, algo);
         return FM_EINVAL;

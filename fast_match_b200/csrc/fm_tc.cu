@@ -37,6 +37,7 @@
 #include <math.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "fm_common.cuh"
 #include "fm_tc_ptx.cuh"
@@ -552,6 +553,10 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
             if (C::EPILOGUE_FREES_SLOT && releases_stage && lane == 0) mbar_arrive(smem_u32(&bars->empty[u % C::STAGES]));
             int bound = min(st.m2, shared_b);
             int thr = (cg - bound) >> 1;        // acc' > thr  <=>  C - 2 acc' < bound
+            // The sweep of one accumulator, in two flavours: per-16-column filter branches while the
+            // rows' bounds are still loose (first tiles of a segment: most chunks pass), one branch
+            // per 32 columns once they are tight (the exact update stays per 16 columns).
+            auto sweep = [&](auto warm) {
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 int v0[32], v1[32];
@@ -590,11 +595,41 @@ __device__ __forceinline__ void k_top2_body(const CUtensorMap &map_q, const CUte
 #elif defined(FM_EXPERIMENT_HALF_LD)   /* timing experiment only: results are wrong */
                 FM_CHUNK(v0, 0) FM_CHUNK(v0 + 16, 16)
 #else
-                FM_CHUNK(v0, 0) FM_CHUNK(v0 + 16, 16) FM_CHUNK(v1, 32) FM_CHUNK(v1 + 16, 48)
+#define FM_SLOW(V, COL, MX)                                                               \
+                if (FM_TRIG(MX)) {                                                           \
+                    const int m2_before = st.m2;                                             \
+                    slow16(V, ck + (pass * 64 + (COL)) * 4, jtile, bound, st);               \
+                    if (st.m2 < m2_before) {                                                 \
+                        red_shared_min_s32(sm2_a, st.m2 + 1);                                \
+                        bound = min(st.m2, bound);                                           \
+                        thr = (cg - bound) >> 1;                                             \
+                    }                                                                        \
+                }
+                if constexpr (decltype(warm)::value) {
+                    // warm rows (most chunks fail the filter): one branch per 32 columns
+                    const int ma = max16(v0), mb = max16(v0 + 16);
+                    if (FM_TRIG(max(ma, mb))) { FM_SLOW(v0, 0, ma) FM_SLOW(v0 + 16, 16, mb) }
+                    const int mc = max16(v1), md = max16(v1 + 16);
+                    if (FM_TRIG(max(mc, md))) { FM_SLOW(v1, 32, mc) FM_SLOW(v1 + 16, 48, md) }
+                } else {
+                    FM_CHUNK(v0, 0) FM_CHUNK(v0 + 16, 16) FM_CHUNK(v1, 32) FM_CHUNK(v1 + 16, 48)
+                }
+#undef FM_SLOW
 #endif
 #undef FM_CHUNK
 #undef FM_TRIG
             }
+            };
+            // Measured (tools/variant_batch.py, round 2): one branch per 32 columns everywhere is
+            // as fast as the per-16 form at 50k x 50k and 2 % faster at 200k x 200k; switching
+            // flavour after the first 16 / 32 / 64 tiles of a segment (FM_VARIANT_HYBRID) sits in between.
+#ifdef FM_VARIANT_HYBRID
+            if (it >= FM_VARIANT_HYBRID) sweep(std::true_type{}); else sweep(std::false_type{});
+#elif defined(FM_VARIANT_PER16)
+            sweep(std::false_type{});
+#else
+            sweep(std::true_type{});
+#endif
 #ifdef FM_TC_PROF
             if (lane == 0) {
                 const long long _te3 = clock64();
