@@ -99,6 +99,7 @@ __device__ __forceinline__ int min32(const int (&v)[32]) {
 }
 // unsigned minimum of key - base over 32 keys (the key equal to base - 1 wraps to the maximum)
 __device__ __forceinline__ unsigned umin32(const int (&v)[32], int base) {
+#ifdef FM_GROUPED_UMIN_TREE
     unsigned t[11];
 #pragma unroll
     for (int i = 0; i < 10; ++i)
@@ -106,6 +107,20 @@ __device__ __forceinline__ unsigned umin32(const int (&v)[32], int base) {
     t[10] = min((unsigned)(v[30] - base), (unsigned)(v[31] - base));
     const unsigned a = umin3i(t[0], t[1], t[2]), b = umin3i(t[3], t[4], t[5]), c = umin3i(t[6], t[7], t[8]);
     return umin3i(umin3i(a, b, c), t[9], t[10]);
+#else
+    // fused add + min (VIADDMNMX.U32: one ALU-pipe op per key instead of a subtraction plus half a
+    // 3-input min); four independent chains keep the dependent-issue latency out of the way
+    const unsigned nb = (unsigned)(-base);
+    unsigned r0 = 0xFFFFFFFFu, r1 = 0xFFFFFFFFu, r2 = 0xFFFFFFFFu, r3 = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        r0 = __viaddmin_u32((unsigned)v[i], nb, r0);
+        r1 = __viaddmin_u32((unsigned)v[8 + i], nb, r1);
+        r2 = __viaddmin_u32((unsigned)v[16 + i], nb, r2);
+        r3 = __viaddmin_u32((unsigned)v[24 + i], nb, r3);
+    }
+    return umin3i(umin3i(r0, r1, r2), r3, r0);
+#endif
 }
 
 // Queries given by index (q_gather) are packed once so that TMA can fetch a round's rows as
@@ -153,7 +168,7 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     unsigned long long *skeys = (unsigned long long *)(smem + SMEM_KEYS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef FM_TC_PROF
-    unsigned long long _gp[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long _gp[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long _gk0 = clock64();
 #endif
 
@@ -416,8 +431,11 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 #pragma unroll 1
             for (int base = 0; base < ncols; base += 32) {
                 int V[32];
+                GP_T(_q0);
                 tmem_ld32(taddr0 + base, V);
                 tmem_ld_wait();
+                GP_T(_q1);
+                GP_ACC(13, _q0, _q1);
                 if (base + 32 >= ncols) {
                     tc_fence_before();
                     __syncwarp();
@@ -453,6 +471,11 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                         }
                     }
                 }
+                GP_T(_q2);
+                GP_ACC(14, _q1, _q2);
+#ifdef FM_TC_PROF
+                _gp[15] += 1;
+#endif
                 const int h1 = min32(V);
                 int h2 = I32_MAX;
                 if (!top1) {
@@ -516,7 +539,7 @@ k_grouped_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     __syncthreads();
 #ifdef FM_TC_PROF
     if (lane == 0 && (warp == 0 || warp == 1 || warp == 4))
-        for (int i = 0; i < 11; ++i) if (_gp[i]) atomicAdd(&g_gprof[i], _gp[i]);
+        for (int i = 0; i < 16; ++i) if (i != 11 && i != 12 && _gp[i]) atomicAdd(&g_gprof[i], _gp[i]);
     if (threadIdx.x == 0) { atomicAdd(&g_gprof[11], (unsigned long long)(clock64() - _gk0)); atomicAdd(&g_gprof[12], 1ull); }
 #endif
     if (warp == 2) {

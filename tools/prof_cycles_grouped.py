@@ -16,3 +16,5 @@ print("ms", a["ms"], "ctas", ctas, "units(all calls)", units, "cycles/cta/call",
 print("producer per unit: wait empty %.0f  own work %.0f" % (v[0] / units, v[1] / units))
 print("mma per unit: wait full %.0f  wait tmem_empty %.0f  issue %.0f" % (v[3] / units, v[4] / units, v[5] / units))
 print("epilogue(warp4 = group 0) per own unit: wait tmem_full %.0f  loads+keys+minima %.0f  state merge %.0f  write-out %.0f" % (v[6] / eu, v[7] / eu, v[8] / eu, v[9] / eu))
+pieces = max(v[15], 1)
+print("  per 32-column piece (warp 4): TMEM load + wait %.0f  keys %.0f  (pieces per own unit %.2f)" % (v[13] / pieces, v[14] / pieces, pieces / eu))
