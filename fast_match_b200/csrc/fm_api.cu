@@ -328,6 +328,8 @@ struct HostCtx {                 // one per device: staging buffers, two streams
     bool ready = false;
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t in_ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    cudaEvent_t t_begin = nullptr, t_up = nullptr;      // bracket the first upload of a call (timing enabled)
+    double h2d_bytes_per_ms = 0.0;                       // measured on the previous calls of this context
     uint8_t *pin_in = nullptr; size_t pin_in_cap = 0;
     uint8_t *pin_out = nullptr; size_t pin_out_cap = 0;
     uint8_t *dev = nullptr; size_t dev_cap = 0;
@@ -377,10 +379,21 @@ int top2_host_locked(HostCtx &c, const uint8_t *q_host, int64_t M, const uint8_t
             FM_CUDA_TRY(cudaEventCreateWithFlags(&c.in_ready[h], cudaEventDisableTiming));
             FM_CUDA_TRY(cudaEventCreateWithFlags(&c.done[h], cudaEventDisableTiming));
         }
+        FM_CUDA_TRY(cudaEventCreate(&c.t_begin));
+        FM_CUDA_TRY(cudaEventCreate(&c.t_up));
         c.ready = true;
     }
-    // two halves only when the second launch's fixed cost is small next to the copy it hides
-    const int halves = (M >= 16384 && N >= 4096) ? 2 : 1;
+    // Two halves pay one more launch sequence (~0.05 ms of fixed cost and cold rows at 50k x 50k) to
+    // hide the upload of the second half of the queries (a quarter of the input bytes): worth it when
+    // this box's PCIe needs more than ~0.36 ms for the whole input (measured: 0.29 ms -> one piece is
+    // 0.05 ms faster, 0.85 ms -> two halves are 0.25 ms faster).  The bandwidth is taken from the
+    // previous calls on this context; the first call assumes a slow link.
+    // (FM_HOST_HALVES=1|2 forces one form, for A/B timing.)
+    static const int halves_override = [] { const char *e = getenv("FM_HOST_HALVES"); return e && *e ? atoi(e) : 0; }();
+    const double in_bytes = (double)(M + N) * FM_DIM;
+    const bool slow_link = c.h2d_bytes_per_ms <= 0.0 || in_bytes / c.h2d_bytes_per_ms > 0.36;
+    const int halves = halves_override == 1 ? 1 : (halves_override == 2 && M >= 1024) ? 2
+                       : (M >= 16384 && N >= 4096 && slow_link) ? 2 : 1;
     const int64_t m0 = halves == 2 ? ((M / 2 + 511) / 512) * 512 : M;      // whole M-blocks in the first half
     const int64_t hm[2] = {m0, M - m0}, hbeg[2] = {0, m0};
     const size_t qb = (size_t)M * FM_DIM, tb = (size_t)N * FM_DIM;
@@ -407,7 +420,12 @@ int top2_host_locked(HostCtx &c, const uint8_t *q_host, int64_t M, const uint8_t
                             (!mask_host || is_device_accessible_host(mask_host));
     if (!out_pinned && (rc = ensure(&c.pin_out, &c.pin_out_cap, o_ws - o_d2, true)) != FM_OK) return rc;
 
+    static const bool trace = [] { const char *e = getenv("FM_HOST_TRACE"); return e && *e && atoi(e) != 0; }();
+    cudaEvent_t tr[8] = {};
+    auto stamp = [&](int i, cudaStream_t st) { if (trace) { cudaEventCreate(&tr[i]); cudaEventRecord(tr[i], st); } };
     *enqueued = true;
+    stamp(0, c.copy);
+    FM_CUDA_TRY(cudaEventRecord(c.t_begin, c.copy));
     if (tb) {
         const uint8_t *src = t_host;
         if (!t_pinned) { memcpy(c.pin_in + o_t, t_host, tb); src = c.pin_in + o_t; }
@@ -419,6 +437,8 @@ int top2_host_locked(HostCtx &c, const uint8_t *q_host, int64_t M, const uint8_t
         if (!q_pinned) { memcpy(c.pin_in + o_q + off, q_host + off, nb); src = c.pin_in + o_q + off; }
         FM_CUDA_TRY(cudaMemcpyAsync(c.dev + o_q + off, src, nb, cudaMemcpyHostToDevice, c.copy));
         FM_CUDA_TRY(cudaEventRecord(c.in_ready[h], c.copy));
+        if (h == 0) FM_CUDA_TRY(cudaEventRecord(c.t_up, c.copy));
+        stamp(1 + h, c.copy);
     }
     uint8_t *out_base = out_pinned ? nullptr : c.pin_out;
     auto dst = [&](void *user, size_t dev_off) -> uint8_t * {
@@ -428,6 +448,7 @@ int top2_host_locked(HostCtx &c, const uint8_t *q_host, int64_t M, const uint8_t
         if (hm[h] == 0) continue;
         const int64_t r0 = hbeg[h], m = hm[h];
         FM_CUDA_TRY(cudaStreamWaitEvent(c.compute, c.in_ready[h], 0));
+        stamp(3 + 2 * h, c.compute);
         uint32_t *d2_dev = (uint32_t *)(c.dev + o_d2) + r0 * 2;
         int32_t *idx_dev = (int32_t *)(c.dev + o_idx) + r0 * 2;
         if (mask_host)     // Lowe ratio test d1/d2 < tau fused into the same launch sequence
@@ -443,6 +464,7 @@ int top2_host_locked(HostCtx &c, const uint8_t *q_host, int64_t M, const uint8_t
             fm::count_launch();
         }
         FM_CUDA_TRY(cudaEventRecord(c.done[h], c.compute));
+        stamp(4 + 2 * h, c.compute);
         // results of this half go back on the copy stream (which has nothing else left to do once
         // the inputs are up) while the compute stream works on the other half
         FM_CUDA_TRY(cudaStreamWaitEvent(c.copy, c.done[h], 0));
@@ -454,9 +476,30 @@ int top2_host_locked(HostCtx &c, const uint8_t *q_host, int64_t M, const uint8_t
         if (mask_host)
             FM_CUDA_TRY(cudaMemcpyAsync(dst(mask_host, o_mask) + r0, c.dev + o_mask + r0, (size_t)m, cudaMemcpyDeviceToHost, c.copy));
     }
+    stamp(7, c.copy);
     FM_CUDA_TRY(cudaStreamSynchronize(c.copy));
     FM_CUDA_TRY(cudaStreamSynchronize(c.compute));
     *enqueued = false;
+    {   // this box's host-to-device bandwidth, for the next call's choice
+        float ms = 0;
+        const double up_bytes = (double)tb + (double)hm[0] * FM_DIM;
+        if (cudaEventElapsedTime(&ms, c.t_begin, c.t_up) == cudaSuccess && ms > 0 && up_bytes >= (1 << 20)) {
+            const double bw = up_bytes / ms;
+            c.h2d_bytes_per_ms = c.h2d_bytes_per_ms > 0 ? 0.5 * (c.h2d_bytes_per_ms + bw) : bw;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
+    if (trace) {
+        const char *nm[8] = {"start", "in0 up", "in1 up", "k0 begin", "k0 done", "k1 begin", "k1 done", "copies done"};
+        for (int i = 1; i < 8; ++i) {
+            if (!tr[i]) continue;
+            float ms = 0;
+            cudaEventElapsedTime(&ms, tr[0], tr[i]);
+            fprintf(stderr, "  [host trace] %-12s %.3f ms\n", nm[i], ms);
+        }
+        for (int i = 0; i < 8; ++i) if (tr[i]) cudaEventDestroy(tr[i]);
+    }
     if (!out_pinned) {
         memcpy(d2_host, c.pin_out, ob_d2);
         memcpy(idx_host, c.pin_out + (o_idx - o_d2), ob_idx);

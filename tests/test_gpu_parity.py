@@ -82,6 +82,30 @@ def test_top2_auto_and_host(cuda):
     assert np.array_equal(hdist, np.sqrt(od2.astype(np.float32)))
 
 
+def test_host_entry_point_two_halves(cuda):
+    """fm_top2_host_u8 on a problem large enough for its overlapped form (queries go up in two halves,
+    the second while the first is matched): pageable and pinned buffers, distances + ratio mask, an odd
+    row count, and a repeat call on the same context -- all equal to the device path and the oracle."""
+    M, N = 20011, 6007
+    q, t = synth.make_pair(M, N, seed=12)
+    d2, idx, ratio, mask = backend.ratio_match(_dev(q, cuda), _dev(t, cuda), 0.8, want_ratio=True)
+    want_d2, want_idx, want_mask = _u32(d2), idx.cpu().numpy(), mask.cpu().numpy()
+    rows = np.r_[0:300, 9900:10400, M - 300:M]
+    od2, oidx = oracle.c_top2(q[rows], t)
+    assert np.array_equal(want_d2[rows], od2) and np.array_equal(want_idx[rows], oidx)
+    for _ in range(2):
+        hd2, hidx, hdist, hmask = backend.top2_host(q, t, want_dist=True, tau=0.8)
+        assert np.array_equal(hd2, want_d2) and np.array_equal(hidx, want_idx)
+        assert np.array_equal(hdist, np.sqrt(want_d2.astype(np.float32))) and np.array_equal(hmask.astype(bool), want_mask)
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    out = (pin(np.empty((M, 2), np.uint32)), pin(np.empty((M, 2), np.int32)), None, pin(np.empty(M, np.uint8)))
+    pd2, pidx, _, pmask = backend.top2_host(pin(q), pin(t), want_dist=False, tau=0.8, out=out)
+    assert np.array_equal(pd2, want_d2) and np.array_equal(pidx, want_idx) and np.array_equal(pmask.astype(bool), want_mask)
+    # no targets at all: every slot missing, mask 0
+    ed2, eidx, _, emask = backend.top2_host(q[:100], t[:0], want_dist=False, tau=0.8)
+    assert (ed2 == 0xFFFFFFFF).all() and (eidx == -1).all() and not emask.any()
+
+
 def test_ratio(cuda):
     q, t = synth.make_pair(4000, 4000, seed=4)
     d2, idx = backend.top2(_dev(q, cuda), _dev(t, cuda))
