@@ -69,3 +69,30 @@ def test_sass_has_blackwell_tensor_and_tma_instructions():
     for mnemonic in ("UTCIMMA", "LDTM", "UTMALDG", "UTCIMMA.2CTA", "UTMALDG.2D.2CTA", "UTCBAR.2CTA.MULTICAST"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in subprocess.run([cuobjdump, "-lelf", build.LIB], capture_output=True, text=True).stdout
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/fastmatch_b200.h compiles as strict C99 and a C program that references every entry
+    point links against libfmatch.so and runs (argument validation only: no GPU involved)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    build.build()
+    names = declared_symbols()
+    src = tmp_path / "cabi_check.c"
+    src.write_text(
+        '#include "fastmatch_b200.h"\n#include <stdio.h>\n#include <string.h>\n'
+        "int main(void) {\n"
+        "    void *fns[] = {" + ", ".join("(void *)%s" % n for n in names) + "};\n"
+        "    int rc = fm_top2_u8(0, -1, 0, 0, 0, 0, 0, 0, 0, 0, FM_ALGO_AUTO, 0);\n"
+        '    printf("%d %d %d\\n", fm_version(), (int)(sizeof(fns) / sizeof(fns[0])), rc);\n'
+        "    return (rc == FM_EINVAL && strstr(fm_last_error(), \"fm_top2_u8\") != 0) ? 0 : 1;\n}\n")
+    exe = tmp_path / "cabi_check"
+    libdir = os.path.dirname(build.LIB)
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src),
+                           "-o", str(exe), "-L" + libdir, "-lfmatch", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.split()[1] == str(len(names))
