@@ -101,6 +101,25 @@ class Grid_Cache(object):
             self.last = self.cache(col, row)
         return self.grid[col][row]
 
+    def cache_many(self, cells, executor=None):
+        """Cache several (col, row) cells at once; with an executor the caching function (per-cell
+        SIFT, cache.pyx:124-138) runs on its threads -- cv2 releases the GIL, every call builds its
+        own detector, and the result per cell is the same as a one-by-one visit.  `last` is left
+        alone: a batched prefetch has no visiting order (the flood fill replays it itself)."""
+        todo = [(col, row) for (col, row) in dict.fromkeys(cells) if row not in self.grid[col]]
+        crops = []
+        for col, row in todo:
+            (x_min, x_max), (y_min, y_max) = self.rect(col, row)
+            crops.append(self.data[y_min:y_max, x_min:x_max, :])
+        if self.fun is None:
+            results = crops
+        elif executor is None or len(crops) < 2:
+            results = [self.fun(c) for c in crops]
+        else:
+            results = list(executor.map(self.fun, crops))
+        for (col, row), res in zip(todo, results):
+            self.grid[col][row] = res
+
     def get(self, x, y):
         if x > self.width or y > self.height:
             raise Exception("(%i,%i) is outside data bounds of (%i,%i)" % (x, y, self.width, self.height))

@@ -32,6 +32,8 @@ Memoised rounds, the cell pool and the cells' features stay resident across `get
 calls of one `match()`.
 """
 import collections
+import concurrent.futures
+import os
 import time
 
 import numpy
@@ -42,6 +44,20 @@ from .cache import Grid_Cache, Metric_Cache  # noqa: F401  (re-exported like the
 
 _EMPTY = (numpy.array([]), numpy.array([]), numpy.array([]))
 MAX_WAVE = 1024       # rounds per grouped launch (bounds the speculation, not the result)
+_EXECUTORS = {}
+
+
+def _executor(threads):
+    """Shared thread pool for the per-cell feature extraction of a wave (None = run inline)."""
+    if threads is None:
+        threads = min(16, os.cpu_count() or 1)
+    threads = int(threads)
+    if threads <= 1:
+        return None
+    ex = _EXECUTORS.get(threads)
+    if ex is None:
+        ex = _EXECUTORS[threads] = concurrent.futures.ThreadPoolExecutor(max_workers=threads, thread_name_prefix="fm-sift")
+    return ex
 
 
 def match(query_cache, target_img, options={}):
@@ -181,6 +197,9 @@ class _Job(object):
         grid_margin = options.get("grid_margin", 25)
         self.radius = int(options.get("radius", 100))
         self.features = options.get("features", matchutil.get_features)
+        # a wave knows all the cells it needs before it needs them, so their SIFT can run on several
+        # host threads at once (the reference extracts one cell per round, fastmatch.pyx:156)
+        self.executor = _executor(options.get("sift_threads"))
         self.stats = options.get("stats") if options.get("stats") is not None else {}
         for k in ("waves", "rounds_evaluated", "launches"):
             self.stats.setdefault(k, 0)
@@ -207,6 +226,7 @@ class _Job(object):
             return
         t0 = time.perf_counter()
         chunks, meta = [], []
+        self.grid.cache_many(new, self.executor)
         for (col, row) in new:
             kp, ds = self.grid.get_cell(col, row)
             u8 = matchutil.to_u8(ds)

@@ -138,6 +138,30 @@ def test_speculation_batches_many_rounds_per_launch(monkeypatch, graf):
     assert stats["rounds_evaluated"] <= 1.5 * ref.rounds                  # bounded speculation waste
 
 
+def test_threaded_cell_features_equal_sequential(monkeypatch, graf):
+    """A wave's new cells are extracted on several host threads (Grid_Cache.cache_many): same
+    features per cell as one-by-one visits (real cv2 SIFT), and the same matches whatever the
+    thread count (frozen features)."""
+    import cv2
+    from fast_match_b200 import matchutil
+    cache, img1 = graf
+    cells = [(c, r) for c in range(3, 7) for r in range(4, 9)]
+    seq = fm_cache.Grid_Cache(img1, (50, 50), matchutil.get_features, margin=25)
+    par = fm_cache.Grid_Cache(img1, (50, 50), matchutil.get_features, margin=25)
+    seq.cache_many(cells, None)
+    par.cache_many(cells + cells[:3], fastmatch._executor(4))          # duplicates are ignored
+    one = fm_cache.Grid_Cache(img1, (50, 50), matchutil.get_features, margin=25)
+    for col, row in cells:
+        (k1, d1), (k2, d2), (k3, d3) = seq.grid[col][row], par.grid[col][row], one.get_cell(col, row)
+        assert [k.pt for k in k1] == [k.pt for k in k2] == [k.pt for k in k3]
+        assert (d1 is None and d2 is None and d3 is None) or (np.array_equal(d1, d2) and np.array_equal(d1, d3))
+    assert par.last is None and one.last == one.rect(*cells[-1])
+    _stub_backend(monkeypatch)
+    a = fastmatch.match(cache, img1, {"features": frozen.features, "sift_threads": 1})(0.9)
+    b = fastmatch.match(cache, img1, {"features": frozen.features, "sift_threads": 8})(0.9)
+    _same_matches(a, b)
+
+
 def test_readme_example_against_frozen_cv2_run(monkeypatch, graf):
     """Config 1: Fast-Match graf img4 -> img1 at tau 0.7 / 0.9 equals the frozen run that used
     cv2.BFMatcher as the matcher.  The inputs are the frozen features (tests/frozen.py), so the test
