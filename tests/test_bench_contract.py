@@ -22,6 +22,11 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+    # both arms describe the workload with the very same dict (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.headline_config(1)
+    assert "per step" in d["cpu_baseline"]["sample"]
 
 
 def test_reference_arm_other_ranks_exit_quietly():
