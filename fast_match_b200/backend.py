@@ -123,9 +123,8 @@ def top2(q, t, t_index_base=0, algo=FM_ALGO_AUTO, want_keys=False, out=None):
     else:
         d2, idx, keys = out
     L = lib()
-    wsb = L.fm_top2_workspace_bytes(M, N)
-    ws = _workspace(dev, wsb)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev):         # (the plan behind the workspace size is per device)
+        ws = _workspace(dev, L.fm_top2_workspace_bytes(M, N))
         _check(L.fm_top2_u8(_ptr(q), M, _ptr(t), N, int(t_index_base), _ptr(d2), _ptr(idx),
                             _ptr(keys), _ptr(ws), ws.numel(), int(algo), _stream(dev)),
                "fm_top2_u8")
@@ -146,8 +145,8 @@ def ratio_match(q, t, tau, algo=FM_ALGO_AUTO, want_ratio=False, out=None):
         d2, idx, mask = out
     r = torch.empty(M, dtype=torch.float64, device=dev) if want_ratio else None
     L = lib()
-    ws = _workspace(dev, L.fm_top2_workspace_bytes(M, N))
     with torch.cuda.device(dev):
+        ws = _workspace(dev, L.fm_top2_workspace_bytes(M, N))
         _check(L.fm_ratio_match_u8(_ptr(q), M, _ptr(t), N, float(tau), _ptr(d2), _ptr(idx), _ptr(r),
                                    _ptr(mask), _ptr(ws), ws.numel(), int(algo), _stream(dev)),
                "fm_ratio_match_u8")
