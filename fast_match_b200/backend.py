@@ -207,6 +207,29 @@ def grouped_mutual(qpool, q_off, tpool, t_off, q_gather=None, t_base=None, max_n
     return d2, idx, t2q, (mutual.view(torch.bool) if want_mutual else None)
 
 
+def mutual_single(q, t):
+    """crossCheck=True, k=1 for ONE (possibly large) pair of sets: (d2 int32 [M] of the nearest
+    target, idx int32 [M], mutual bool [M]).  The grouped kernel gives a group to a single CTA, which
+    is right for thousands of small rounds but slow for one big group (match_thumbs: 2426 x 1058 on
+    one SM), so a big pair runs the dense kernel in both directions instead; ties go to the lowest
+    index both ways, as in the grouped kernel and in cv2's crossCheck."""
+    q, t = _desc(q, "q"), _desc(t, "t")
+    M, N = q.shape[0], t.shape[0]
+    dev = q.device
+    if M == 0 or N == 0:
+        return (torch.full((M,), NONE_D2, dtype=torch.int32, device=dev), torch.full((M,), -1, dtype=torch.int32, device=dev),
+                torch.zeros(M, dtype=torch.bool, device=dev))
+    if M * N < (1 << 16):
+        off = torch.tensor([[0, M], [0, N]], dtype=torch.int64, device=dev)
+        d2, idx, _, mutual = grouped_mutual(q, off[0], t, off[1], max_nq=M, total_q=M, total_t=N)
+        return d2[:, 0], idx[:, 0], mutual
+    d2, idx = top2(q, t)
+    _, back = top2(t, q)
+    fwd = idx[:, 0].long()
+    mutual = back[fwd, 0] == torch.arange(M, device=dev, dtype=torch.int32)
+    return d2[:, 0], idx[:, 0], mutual
+
+
 def merge_top2(keys, want_unpacked=True):
     """keys int64 [S, M, 2] (uint64 bit patterns) -> (out_keys [M,2], d2 [M,2], idx [M,2])."""
     assert keys.is_cuda and keys.dtype == torch.int64 and keys.dim() == 3 and keys.shape[2] == 2

@@ -100,13 +100,11 @@ def _mutual_pairs(q_dev, t_dev):
     M, N = q_dev.shape[0], t_dev.shape[0]
     if M == 0 or N == 0:
         return numpy.zeros(0, numpy.int64), numpy.zeros(0, numpy.int64), numpy.zeros(0, numpy.float32)
-    off = torch.tensor([[0, M], [0, N]], dtype=torch.int64, device=q_dev.device)
-    d2, idx, _, mutual = backend.grouped_mutual(q_dev, off[0], t_dev, off[1], max_nq=M,
-                                                total_q=M, total_t=N)
+    d2, idx, mutual = backend.mutual_single(q_dev, t_dev)
     keep = torch.nonzero(mutual).flatten()
     qi = keep.cpu().numpy()
-    ti = idx[keep, 0].cpu().numpy().astype(numpy.int64)
-    dist = numpy.sqrt(d2[keep, 0].cpu().numpy().view(numpy.uint32).astype(numpy.float32))
+    ti = idx[keep].cpu().numpy().astype(numpy.int64)
+    dist = numpy.sqrt(d2[keep].cpu().numpy().view(numpy.uint32).astype(numpy.float32))
     return qi, ti, dist
 
 

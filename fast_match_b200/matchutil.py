@@ -108,11 +108,9 @@ def _knn(dt1, dt2, k, cross_check, device=None):
     if k not in (1, 2):
         raise ValueError("only k = 1 or 2 is supported by the top-2 matcher")
     if cross_check:
-        off_q = torch.tensor([0, M], dtype=torch.int64, device=q.device)
-        off_t = torch.tensor([0, N], dtype=torch.int64, device=q.device)
-        d2, idx, _, mutual = backend.grouped_mutual(q, off_q, t, off_t, max_nq=M, total_q=M, total_t=N)
-        d2 = d2[:, :1].cpu().numpy().view(numpy.uint32).astype(numpy.int64)
-        idx = idx[:, :1].cpu().numpy()
+        d2, idx, mutual = backend.mutual_single(q, t)
+        d2 = d2[:, None].cpu().numpy().view(numpy.uint32).astype(numpy.int64)
+        idx = idx[:, None].cpu().numpy()
         valid = mutual.cpu().numpy()[:, None]
     else:
         d2, idx = backend.top2(q, t)

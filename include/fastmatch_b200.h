@@ -114,6 +114,11 @@ int fm_ratio_f32sqrt(const uint32_t *num_d2, int64_t num_stride, const uint32_t 
  * when t_base != NULL, else total_t is used); max_nq = an upper bound on the number of queries
  * of any group (host-known; avoids a device->host sync).  algo: FM_ALGO_AUTO picks the
  * tcgen05 kernel on sm_100; FM_ALGO_MMA_SYNC forces the warp-MMA kernel.
+ * Every descriptor is read from HBM once (the squared norms are summed in the kernel).
+ * A group is processed by ONE thread block (the path is built for thousands of small rounds):
+ * for a single large pair of sets (match_thumbs, bf_match(crossCheck=True) on whole images) two
+ * fm_top2_u8 calls, q->t and t->q, give the same mutual pairs an order of magnitude faster
+ * (fast_match_b200.backend.mutual_single does that above 2^16 pairs).
  */
 size_t fm_grouped_workspace_bytes(int64_t total_q, int64_t total_t, int64_t tpool_rows, int32_t G);
 int fm_grouped_mutual_u8(const uint8_t *qpool, const int32_t *q_gather, const int64_t *q_off,

@@ -82,6 +82,29 @@ def test_top2_auto_and_host(cuda):
     assert np.array_equal(hdist, np.sqrt(od2.astype(np.float32)))
 
 
+def test_mutual_single_big_pair_equals_grouped_and_oracle(cuda):
+    """crossCheck for one big pair (two dense launches) == the grouped kernel with G = 1 == the oracle,
+    including exact duplicates on both sides (ties to the lowest index in both directions)."""
+    q, t = synth.make_pair(2500, 1100, seed=21)
+    t[5:15] = t[700:710]
+    q[100:110] = q[3:13]
+    qd, td = _dev(q, cuda), _dev(t, cuda)
+    d2, idx, mutual = backend.mutual_single(qd, td)
+    off = torch.tensor([[0, len(q)], [0, len(t)]], dtype=torch.int64, device=cuda)
+    gd2, gidx, _, gmut = backend.grouped_mutual(qd, off[0], td, off[1])
+    assert torch.equal(d2, gd2[:, 0]) and torch.equal(idx, gidx[:, 0]) and torch.equal(mutual, gmut)
+    od2, oidx, ot2q = oracle.np_mutual(q, t)
+    keep = oracle.mutual_pairs(oidx, ot2q)
+    assert np.array_equal(np.nonzero(mutual.cpu().numpy())[0], keep)
+    assert np.array_equal(_u32(d2), od2[:, 0]) and np.array_equal(idx.cpu().numpy(), oidx[:, 0])
+    # tiny pair: stays on the grouped kernel
+    s2, si, sm = backend.mutual_single(qd[:40], td[:30])
+    sd2, sidx, st2q = oracle.np_mutual(q[:40], t[:30])
+    assert np.array_equal(np.nonzero(sm.cpu().numpy())[0], oracle.mutual_pairs(sidx, st2q)) and np.array_equal(si.cpu().numpy(), sidx[:, 0])
+    e = backend.mutual_single(qd[:7], td[:0])
+    assert not e[2].any() and (e[1] == -1).all()
+
+
 def test_host_entry_point_two_halves(cuda):
     """fm_top2_host_u8 on a problem large enough for its overlapped form (queries go up in two halves,
     the second while the first is matched): pageable and pinned buffers, distances + ratio mask, an odd
