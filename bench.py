@@ -702,6 +702,33 @@ def sharded_leg(args, dev, world, rank, backend, sharded, barrier, max_over_rank
     except Exception as ex:  # noqa: BLE001
         out["parity_sample_ok"] = None
         out["parity_sample_error"] = repr(ex)
+    # ---- the same job on a (query groups x target shards) grid, reported beside the plain target sharding
+    #      above (which stays `ms` / `value`): 2 x world/2 sweeps half as many target shards per query row,
+    #      so every rank does the same amount of tensor work with half-as-deep cold starts and the exchange
+    #      stays inside a group.  world = 2: 2 x 1 is pure query sharding (no exchange), listed for completeness.
+    if world >= 2 and world % 2 == 0:
+        try:
+            grid = sharded.Grid2D(query_groups=2)
+            g_lo, g_hi = grid.target_range(Ntot)
+            t2 = t if (g_lo, g_hi) == (lo, hi) else plant_torch(q, siftlike_torch(g_lo, g_hi, 22, dev), g_lo, 23)
+            step2 = lambda: grid.ratio_match(q, t2, Ntot, TAU)
+            step2(); barrier()
+            t2s = []
+            for _ in range(3):
+                flush.zero_()
+                barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); idx2, d22, _, mask2 = step2(); b.record()
+                barrier()
+                t2s.append(max_over_ranks(a.elapsed_time(b)))
+            ms2 = sorted(t2s)[len(t2s) // 2]
+            n2 = mask2.sum().to(torch.int64)
+            dist.all_reduce(n2)
+            out["grid_2d"] = {"arrangement": "%d query groups x %d target shards" % (grid.Sq, grid.St), "ms": ms2,
+                              "value": Mtot / (ms2 * 1e-3), "matched_queries": int(n2.item())}
+            del t2
+        except Exception as ex:  # noqa: BLE001
+            out["grid_2d"] = {"error": repr(ex)}
     # ---- same-run, same-box denominator of the strong-scaling curve: rank 0 alone, unsharded
     if world > 1:
         ms1 = 0.0
@@ -725,6 +752,8 @@ def sharded_leg(args, dev, world, rank, backend, sharded, barrier, max_over_rank
         out["ms_1gpu_same_run"] = ms1
         out["efficiency"] = ms1 / (world * ms)
         out["speedup_vs_1gpu_same_run"] = ms1 / ms
+        if isinstance(out.get("grid_2d"), dict) and "ms" in out["grid_2d"]:
+            out["grid_2d"]["efficiency"] = ms1 / (world * out["grid_2d"]["ms"])
     # ---- the reference's CPU matcher on this shape: cv2.BFMatcher refuses >= 2^18 train rows, so the targets
     #      go in <= 262143-row chunks with a host merge; 4096 sampled queries, extrapolated linearly in M
     if with_cpu:

@@ -72,14 +72,14 @@ def sharded_top2(q, t_shard, t_index_base, group=None, local_top2=_local_top2_ke
 
 
 def sharded_top2_sliced(q, t_shard, t_index_base, group=None, local_top2=_local_top2_keys, merge=_merge,
-                        recv_buf=None):
+                        recv_buf=None, world_rank=None):
     """Exact global top-2 of THIS RANK'S SLICE of the query rows.
 
     Returns ((q_lo, q_hi), merged) with merged = merge(keys [S, q_hi - q_lo, 2]) for the rows
     shard_range(M, rank, S): rank p receives from every rank the candidates of p's rows only
     (all_to_all_single with row splits), i.e. M x 16 bytes in total instead of S x M x 16.
     """
-    world, rank = _world(group)
+    world, rank = world_rank if world_rank is not None else _world(group)
     keys = local_top2(q, t_shard, t_index_base)            # int64 [M,2]
     M = keys.shape[0]
     if world == 1:
@@ -92,6 +92,56 @@ def sharded_top2_sliced(q, t_shard, t_index_base, group=None, local_top2=_local_
     dist.all_to_all_single(recv_buf, keys.contiguous(), output_split_sizes=[mine] * world,
                            input_split_sizes=sizes, group=group)
     return splits[rank], merge(recv_buf.view(world, mine, 2))
+
+
+class Grid2D(object):
+    """A (query groups x target shards) arrangement of the ranks: rank r = g * St + s matches the
+    queries of group g (rows shard_range(M, g, Sq)) against target shard s of St (rows
+    shard_range(N, s, St)); the packed-key exchange and the merge stay inside the St ranks of a
+    group.  Sq = 1 is plain target sharding.  More target shards mean less memory per GPU but also
+    more rows swept from no bound (every shard pays its rows' ~2 ln(shard size) exact updates) and a
+    wider exchange; at 1M x 1M on 8 GPUs a 2 x 4 grid does the same work per rank as 1 x 8 with
+    half-as-deep cold starts.  Build it on every rank (new_group is collective)."""
+
+    def __init__(self, query_groups=1, backend=None):
+        self.world, self.rank = _world(None)
+        if self.world % query_groups:
+            raise ValueError("query_groups must divide the world size")
+        self.Sq, self.St = int(query_groups), self.world // int(query_groups)
+        self.g, self.s = divmod(self.rank, self.St)
+        self.group = None
+        if self.world > 1 and self.Sq > 1:
+            for g in range(self.Sq):                      # every rank creates every group, in the same order
+                grp = dist.new_group(list(range(g * self.St, (g + 1) * self.St)), backend=backend)
+                if g == self.g:
+                    self.group = grp
+
+    def target_range(self, N):
+        return shard_range(N, self.s, self.St)
+
+    def query_range(self, M):
+        return shard_range(M, self.g, self.Sq)
+
+    def my_rows(self, M):
+        """Global query rows whose final result this rank holds after ratio_match."""
+        q_lo, q_hi = self.query_range(M)
+        lo, hi = shard_range(q_hi - q_lo, self.s, self.St)
+        return q_lo + lo, q_lo + hi
+
+    def top2_sliced(self, q, t_shard, N, local_top2=_local_top2_keys, merge=_merge):
+        """q: ALL queries (replicated); t_shard: this rank's target rows target_range(N).
+        Returns (my_rows(M), merged top-2 of those rows)."""
+        M = q.shape[0]
+        q_lo, q_hi = self.query_range(M)
+        (lo, hi), merged = sharded_top2_sliced(q[q_lo:q_hi], t_shard, self.target_range(N)[0], group=self.group,
+                                               local_top2=local_top2, merge=merge, world_rank=(self.St, self.s))
+        return (q_lo + lo, q_lo + hi), merged
+
+    def ratio_match(self, q, t_shard, N, tau, want_ratio=False):
+        """(idx, d2, ratio | None, mask) of the query rows my_rows(M)."""
+        _, (_, d2, idx) = self.top2_sliced(q, t_shard, N)
+        ratio, mask = backend.ratio(d2[:, 0], den_d2=d2[:, 1], tau=tau, want_ratio=want_ratio)
+        return idx, d2, ratio, mask
 
 
 def gather_full(x_slice, M, group=None):
@@ -111,14 +161,14 @@ def gather_full(x_slice, M, group=None):
     return full.view(torch.bool) if as_bool else full
 
 
-def ratio_match_sharded(q, t_shard, t_index_base, tau, group=None, want_ratio=True, full=False):
+def ratio_match_sharded(q, t_shard, t_index_base, tau, group=None, want_ratio=True, full=False, world_rank=None):
     """Ratio-Match (Classic Matching.ipynb cell 3) over a sharded target set.
 
     Returns (idx [m,2] global target rows, d2 [m,2], ratio float64 [m] | None, mask bool [m]) for
     this rank's slice of the queries (rows shard_range(M, rank, S); m = its length), or for all
     M queries on every rank when full=True."""
     M = q.shape[0]
-    _, (_, d2, idx) = sharded_top2_sliced(q, t_shard, t_index_base, group=group)
+    _, (_, d2, idx) = sharded_top2_sliced(q, t_shard, t_index_base, group=group, world_rank=world_rank)
     ratio, mask = backend.ratio(d2[:, 0], den_d2=d2[:, 1], tau=tau, want_ratio=want_ratio)
     if full:
         idx, d2, mask = gather_full(idx, M, group), gather_full(d2, M, group), gather_full(mask, M, group)

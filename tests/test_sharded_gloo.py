@@ -66,3 +66,48 @@ def test_two_rank_sharded_top2_equals_unsharded():
         q_lo, q_hi, sl = out[("slice", r)]
         assert np.array_equal(sl, want[q_lo:q_hi])
         assert np.array_equal(out[("full", r)], want)
+
+
+def _worker_2d(rank, world, port, q, t, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def local_top2(qq, ts, base):
+            d2, idx = oracle.c_top2(qq.numpy(), ts.numpy(), base)
+            return torch.from_numpy(oracle.pack_keys(d2, idx).view(np.int64))
+
+        def merge(g):
+            return torch.from_numpy(oracle.c_merge_top2(g.numpy().view(np.uint64)).view(np.int64))
+
+        for sq in (1, 2, 4):
+            grid = sharded.Grid2D(query_groups=sq, backend="gloo")
+            lo, hi = grid.target_range(len(t))
+            rows, merged = grid.top2_sliced(torch.from_numpy(q), torch.from_numpy(t[lo:hi]), len(t),
+                                            local_top2=local_top2, merge=merge)
+            assert rows == grid.my_rows(len(q))
+            out[(sq, rank)] = (rows, merged.numpy().view(np.uint64).copy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_four_rank_2d_grid_equals_unsharded():
+    """world 4 over gloo as 1 x 4 (plain target sharding), 2 x 2 and 4 x 1 (query groups x target
+    shards): every arrangement tiles the query rows exactly once with the unsharded answer."""
+    q, t = synth.make_pair(403, 610, seed=8)
+    t[3:9] = t[300:306]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_2d, args=(4, port, q, t, out), nprocs=4, join=True)
+    d2, idx = oracle.c_top2(q, t)
+    want = oracle.pack_keys(d2, idx)
+    for sq in (1, 2, 4):
+        covered = np.zeros(len(q), bool)
+        for r in range(4):
+            (lo, hi), got = out[(sq, r)]
+            assert np.array_equal(got, want[lo:hi]), (sq, r)
+            assert not covered[lo:hi].any()
+            covered[lo:hi] = True
+        assert covered.all()
