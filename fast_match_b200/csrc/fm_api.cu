@@ -366,9 +366,10 @@ struct DeviceGuard {             // the caller's current device is restored on e
 };
 
 // Body of fm_top2_host_u8 (runs with the context locked and the device selected).
-// The queries go up in two halves on a copy stream while the compute stream already matches the
-// first half against the targets; each half's results go back while the other half computes.
-// Row halves are independent, so nothing has to be merged.
+// Copies run on a copy stream, kernels on a compute stream.  On a slow host link the queries go up
+// in two halves: the compute stream matches the first half against the targets while the second is
+// still being copied, and each half's results go back while the other half computes (row halves
+// are independent, so nothing has to be merged); on a fast link everything goes up in one piece.
 int top2_host_locked(HostCtx &c, const uint8_t *q_host, int64_t M, const uint8_t *t_host, int64_t N,
                      uint32_t *d2_host, int32_t *idx_host, float *dist_host, double tau, uint8_t *mask_host,
                      bool *enqueued) {

@@ -144,6 +144,10 @@ int fm_merge_top2(const uint64_t *keys, int32_t S, int64_t M, uint64_t *out_keys
  * mask (nullable) [M] uint8 = Lowe ratio test dist[i][0] / dist[i][1] < tau (Classic
  * Matching.ipynb cell 3 JSON :65), computed on the device in the same call.
  * Pinned / cudaHostRegister'ed caller buffers are used directly; pageable ones are staged.
+ * One context (two streams, staging buffers) per device; the caller's current device is restored.
+ * The library measures the upload rate of its previous calls on the device and, where the link is
+ * slow, uploads the queries in two halves so that the second half travels under the first half's
+ * compute (FM_HOST_HALVES=1|2 in the environment forces one form).
  */
 int fm_top2_host_u8(const uint8_t *q_host, int64_t M, const uint8_t *t_host, int64_t N,
                     uint32_t *d2_host, int32_t *idx_host, float *dist_host, double tau,
