@@ -39,6 +39,30 @@ SHAPES = [(1, 1), (1, 300000), (3, 70001), (255, 255), (257, 513), (513, 255), (
 
 @pytest.mark.parametrize("M,N", SHAPES)
 def test_stream_k_partition(M, N):
+    check_plan(M, N)
+
+
+def test_stream_k_partition_random_shapes():
+    """The same invariants on seeded random shapes (log-uniform sizes up to 2M x 2M)."""
+    import random
+    rng = random.Random(2024)
+    for _ in range(150):
+        M = int(2 ** rng.uniform(0, 21))
+        N = int(2 ** rng.uniform(0, 21))
+        check_plan(M, N)
+
+
+@pytest.mark.gpu
+def test_stream_k_partition_on_the_device(cuda):
+    """On the GPU box the plan uses the CTA-pair kernel (512-row M-blocks, 74 workers): same invariants."""
+    import random
+    rng = random.Random(7)
+    assert plan(50000, 50000)["pair"] == 1 and plan(50000, 50000)["mblock_rows"] == 512
+    for M, N in SHAPES + [(int(2 ** rng.uniform(8, 21)), int(2 ** rng.uniform(8, 21))) for _ in range(60)]:
+        check_plan(M, N)
+
+
+def check_plan(M, N):
     p = plan(M, N)
     rows, mblocks, ntiles, W = p["mblock_rows"], p["mblocks"], p["ntiles"], p["workers"]
     assert rows in (256, 512) and mblocks == -(-M // rows) and ntiles == -(-N // 256)
