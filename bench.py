@@ -782,7 +782,6 @@ def sharded_leg(args, dev, world, rank, backend, sharded, barrier, max_over_rank
     if with_cpu:
         try:
             import cv2
-            import oracle
             cv2.setNumThreads(os.cpu_count() or 1)
             sample = 4096
             rows = torch.linspace(0, Mtot - 1, sample).long().to(dev)
